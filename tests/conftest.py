@@ -1,0 +1,49 @@
+import os
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+GOLDEN_DIR = os.path.join(ROOT, "tests", "golden")
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
+
+
+def golden_names():
+    return sorted(f[:-4] for f in os.listdir(GOLDEN_DIR) if f.endswith(".npz") and not f.startswith("pe_"))
+
+
+def load_golden(name):
+    import numpy as np
+    import torch
+
+    z = np.load(os.path.join(GOLDEN_DIR, name + ".npz"))
+    cfg = {}
+    for k, v in zip(z["cfg_keys"], z["cfg_vals"]):
+        k, v = str(k), str(v)
+        if k == "conditioning":
+            cfg[k] = v
+        elif k == "dropout":
+            cfg[k] = float(v)
+        else:
+            cfg[k] = int(v)
+    params = {k[len("param::"):]: torch.from_numpy(z[k]) for k in z.files if k.startswith("param::")}
+    grads = {k[len("grad::"):]: torch.from_numpy(z[k]) for k in z.files if k.startswith("grad::")}
+    g = dict(cfg=cfg, params=params, grads=grads,
+             tokens=torch.from_numpy(z["tokens"]), cond=torch.from_numpy(z["cond"]),
+             target=torch.from_numpy(z["target"]),
+             logits_fp32=torch.from_numpy(z["logits_fp32"]), logits_bf16=torch.from_numpy(z["logits_bf16"]),
+             loss_fp32=float(z["loss_fp32"]), pe_table=torch.from_numpy(z["pe_table"]),
+             mask=torch.from_numpy(z["mask"]),
+             decode={int(t): torch.from_numpy(z[f"decode_last::{int(t)}"]) for t in z["decode_prefix_lens"]})
+    return g
+
+
+@pytest.fixture(params=golden_names())
+def golden(request):
+    return load_golden(request.param)
