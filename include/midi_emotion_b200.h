@@ -1,0 +1,242 @@
+/* midi_emotion_b200.h -- C ABI of the B200-native hot path of serkansulun/midi-emotion.
+ *
+ * The reference has no FFI: its model path is Python calling stock PyTorch operators
+ * (SURVEY.md 2.2).  Each entry point below replaces one group of those operator call sites;
+ * the reference lines are cited per function (paths relative to /root/reference/src).
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless the name ends in _host;
+ *   - `stream` is a cudaStream_t passed as void*; all calls only enqueue work (async);
+ *   - return value 0 = ok, non-zero = error; text via me_last_error(); nothing throws;
+ *   - the library owns no persistent device memory: callers (PyTorch) allocate everything;
+ *   - "T" tensors are ME_F32 or ME_BF16 as selected by `dtype`; biases, LayerNorm affine
+ *     parameters, statistics and the residual stream are always fp32;
+ *   - matrices are row-major.  There is no CPU fallback: shape/alignment violations are errors.
+ */
+#ifndef MIDI_EMOTION_B200_H
+#define MIDI_EMOTION_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ME_F32 0
+#define ME_BF16 1
+
+/* conditioning modes (config.py:7-9) */
+#define ME_COND_NONE 0
+#define ME_COND_DISCRETE_TOKEN 1
+#define ME_COND_CONTINUOUS_TOKEN 2
+#define ME_COND_CONTINUOUS_CONCAT 3
+
+/* attention implementations */
+#define ME_ATTN_SIMT 0    /* exact-order fp32 SIMT kernels (fp32 parity path, any dtype) */
+#define ME_ATTN_TENSOR 1  /* bf16 tensor-core kernels */
+
+/* GEMM epilogue flags */
+#define ME_EPI_BIAS 1        /* += bias[n] (fp32)                          */
+#define ME_EPI_RELU 2        /* max(.,0)                                   */
+#define ME_EPI_ADD_F32 4     /* += addend[m, n] (fp32, ld = ldd)           */
+#define ME_EPI_RELU_MASK 8   /* zero where mask[m, n] <= 0 (T, ld = ldmask) */
+
+const char* me_last_error(void);
+int me_version(void);
+/* 1 when the running device is sm_100 (B200); the tcgen05 paths refuse to run otherwise. */
+int me_device_is_sm100(void);
+
+/* ---------------------------------------------------------------------------------------
+ * Input stage.  Replaces models/music_multi.py:89-102 (generate_mask, Embedding, *sqrt(d-dc),
+ * fc_condition, expand+cat, += positional table, dropout) and
+ * models/music_continuous_token.py:81-100 (two Linear(1,d) prefix vectors, cat along sequence).
+ *   tokens   int64 [B, L]            cond  f32 [B, 2] (never read when mode is none/discrete)
+ *   emb_w    f32 [V, d - d_cond]     pe    f32 [max_seq, d]
+ *   cw0/cb0  concat: fc_condition.weight [d_cond, 2] / bias [d_cond]
+ *            ctoken: fc_condition.0.weight [d, 1] / bias [d];  cw1/cb1: fc_condition.1.*
+ *   x_f32    out f32 [B, Ls, d]  (Ls = L + 2 for continuous_token, else L)
+ *   x_T      out T   [B, Ls, d]  (may be NULL, or alias x_f32 when dtype == ME_F32)
+ *   keypad   out u8  [B, Ls]     1 where the key is a pad token (mask[b,q,k] = k>q || keypad[b,k])
+ * ------------------------------------------------------------------------------------- */
+int me_embed_forward(const int64_t* tokens, const float* cond, const float* emb_w, const float* cw0,
+                     const float* cb0, const float* cw1, const float* cb1, const float* pe, int B, int L,
+                     int d, int d_cond, int V, int mode, int pad_token, float dropout_p, uint64_t seed,
+                     int dtype, float* x_f32, void* x_T, uint8_t* keypad, void* stream);
+
+/* Gradient of the input stage w.r.t. embedding.weight and fc_condition.* (autograd of the
+ * lines above; train.py:317).  d_emb, d_cw0/1 and d_cb0/1 are fp32 and must be zeroed by the
+ * caller (they accumulate). */
+int me_embed_backward(const float* dx, const int64_t* tokens, const float* cond, int B, int L, int d,
+                      int d_cond, int V, int mode, int pad_token, float dropout_p, uint64_t seed,
+                      float* d_emb, float* d_cw0, float* d_cb0, float* d_cw1, float* d_cb1, void* stream);
+
+/* ---------------------------------------------------------------------------------------
+ * Linear layers.  D[M,N] = A . B^T (+ epilogue).  Replaces every torch.nn.Linear on the path
+ * (music_multi.py:196-206,237,131-132,106) and their autograd (dgrad / wgrad).
+ *   a_mn = 0: A is [M, K] with K contiguous (lda = row pitch);  a_mn = 1: A is stored [K, M].
+ *   b_mn = 0: B is [N, K] with K contiguous;                    b_mn = 1: B is stored [K, N].
+ *   out_dtype selects D's type.  bf16: tcgen05 + TMA (sm_100a).  f32: exact-order SIMT.
+ * ------------------------------------------------------------------------------------- */
+int me_gemm_bf16(const void* A, const void* B, void* D, int M, int N, int K, int lda, int ldb, int ldd,
+                 int a_mn, int b_mn, int out_dtype, int epi_flags, const float* bias, const float* addend,
+                 const void* relu_mask, int ldmask, void* stream);
+int me_gemm_f32(const float* A, const float* B, float* D, int M, int N, int K, int lda, int ldb, int ldd,
+                int a_mn, int b_mn, int epi_flags, const float* bias, const float* addend,
+                const float* relu_mask, int ldmask, void* stream);
+
+/* ---------------------------------------------------------------------------------------
+ * out = LayerNorm(x_res + dropout(y)) ; post-LN residual block tail (music_multi.py:128-129,
+ * 133-134; eps 1e-6).  y is T, everything else fp32.  z/mean/rstd are saved for backward when
+ * non-NULL.  out_T may be NULL (or alias out_f32 for ME_F32).
+ * ------------------------------------------------------------------------------------- */
+int me_add_layernorm_forward(const float* x_res, const void* y, int dtype, const float* gamma,
+                             const float* beta, float eps, int M, int d, float dropout_p, uint64_t seed,
+                             float* out_f32, void* out_T, float* z, float* mean, float* rstd, void* stream);
+/* dz = dLN(dout); d_gamma/d_beta accumulate (+=, caller zeroes).  dz_f32 feeds the residual
+ * branch, dy_T = dropout_mask * dz feeds the sub-layer GEMMs.  dout_add (optional) is added to
+ * dout first (the residual gradient that bypassed the following sub-layer). */
+int me_add_layernorm_backward(const float* dout, const float* dout_add, const float* z, const float* mean,
+                              const float* rstd, const float* gamma, int M, int d, float dropout_p,
+                              uint64_t seed, int dtype, float* dz_f32, void* dy_T, float* d_gamma,
+                              float* d_beta, void* stream);
+
+/* column sums (bias gradients): out[n] += sum_m X[m, n]; X is T with row pitch ldx. */
+int me_colsum(const void* X, int dtype, int M, int N, int ldx, float* out, void* stream);
+/* dst (T_dst, pitch ld_dst) = src (T_src, pitch ld_src), [rows, cols]; pad columns are zeroed. */
+int me_convert_2d(const void* src, int src_dtype, int ld_src, void* dst, int dst_dtype, int ld_dst, int rows,
+                  int cols, void* stream);
+
+/* ---------------------------------------------------------------------------------------
+ * Relative global attention (Music Transformer), causal + key-pad mask, fused:
+ *   S[i,j] = (q_i.k_j + q_i.E[max_seq-1-(i-j)]) / sqrt(dh),  j <= i and !keypad[b,j]
+ *   O = softmax(S) V
+ * Replaces music_multi.py:211-235 (_get_left_embedding, einsum, _qe_masking, _skewing, QK^T,
+ * mask add, softmax, .V, head merge).  q/k/v are addressed with element strides so that they
+ * may live in a packed QKV buffer [B, Lq, 3, H, dh] or in a KV cache [B, H, T, dh].
+ *   q_pos0: absolute position of query row 0 (0 for full sequences, t for a decode step)
+ *   Lq query rows per sequence, Lk keys per sequence (Lk = q_pos0 + Lq for self-attention)
+ *   out [B, Lq, H*dh] T (pitch out_ld per row), lse f32 [B, H, Lq] (may be NULL when impl=SIMT)
+ * ------------------------------------------------------------------------------------- */
+typedef struct me_attn_args {
+  int32_t dtype, impl;
+  int32_t B, H, Lq, Lk, dh, max_seq, q_pos0, _pad;
+  const void *q, *k, *v, *E;
+  int64_t q_sb, q_sh, q_si; /* element strides: batch, head, row */
+  int64_t k_sb, k_sh, k_sj;
+  int64_t v_sb, v_sh, v_sj;
+  const uint8_t* keypad; /* [B, keypad_ld] or NULL */
+  int64_t keypad_ld;
+  void* out;
+  int64_t o_sb, o_si; /* out[b, i, h*dh + c] = out + b*o_sb + i*o_si + h*dh + c */
+  float* lse;
+  /* optional device-resident position (CUDA-graph friendly decode): when non-NULL,
+   * q_pos0 = *pos_dev and Lk = *pos_dev + Lq are read on the device. */
+  const int32_t* pos_dev;
+  void* stream;
+} me_attn_args;
+int me_attention_forward(const me_attn_args* a);
+
+/* Backward of the above (full self-attention only, q_pos0 = 0, Lq = Lk).
+ *   dout T same addressing as out; dq/dk/dv T with the q/k/v strides; dE f32 [max_seq, dh]
+ *   accumulates (+=, caller zeroes); dsum f32 [B,H,Lq] is scratch. */
+typedef struct me_attn_bwd_args {
+  me_attn_args f;
+  const void* dout;
+  void *dq, *dk, *dv;
+  float* dE;
+  float* dsum;
+} me_attn_bwd_args;
+int me_attention_backward(const me_attn_bwd_args* a);
+
+/* ---------------------------------------------------------------------------------------
+ * One encoder layer (music_multi.py:126-135): attention block + FFN block, post-LN.
+ * Weights: Wqkv = [Wq;Wk;Wv] packed [3d, d] T, E T [max_seq, dh], Wo [d,d], W1 [di,d], W2 [d,di];
+ * biases / LN affine fp32.  Saved tensors are consumed by me_layer_backward.
+ * ------------------------------------------------------------------------------------- */
+typedef struct me_layer_args {
+  int32_t dtype, attn_impl, training, _pad0;
+  int32_t B, Ls, d, H, d_inner, max_seq;
+  float dropout_p, ln_eps;
+  uint64_t seed;
+  /* inputs */
+  const float* x_f32;
+  const void* x_T;
+  const uint8_t* keypad;
+  /* weights */
+  const void* Wqkv;
+  const float* bqkv;
+  const void* E;
+  const void* Wo;
+  const float* bo;
+  const float *ln1_w, *ln1_b;
+  const void* W1;
+  const float* b1;
+  const void* W2;
+  const float* b2;
+  const float *ln2_w, *ln2_b;
+  /* activations: saved (training) or scratch */
+  void* qkv;      /* T [M, 3d] */
+  void* attn_o;   /* T [M, d]  */
+  float* lse;     /* [B, H, Ls] */
+  void* proj;     /* T [M, d] scratch (attention out-proj, later FFN_suf output) */
+  float* z1;      /* [M, d] pre-LN1 sum, NULL in eval */
+  float *mean1, *rstd1;
+  float* out1_f32;
+  void* out1_T;
+  void* h;        /* T [M, d_inner] */
+  float* z2;
+  float *mean2, *rstd2;
+  float* out2_f32;
+  void* out2_T;
+  void* stream;
+} me_layer_args;
+int me_layer_forward(const me_layer_args* a);
+
+typedef struct me_layer_bwd_args {
+  me_layer_args f;      /* same tensors as the forward call */
+  const float* d_out;   /* [M, d] fp32 gradient w.r.t. the layer output */
+  float* d_x;           /* [M, d] fp32 gradient w.r.t. the layer input  */
+  /* parameter gradients, fp32, written (not accumulated) except dE which must be zeroed */
+  float *dWqkv, *dbqkv, *dE, *dWo, *dbo, *dln1_w, *dln1_b, *dW1, *db1, *dW2, *db2, *dln2_w, *dln2_b;
+  /* scratch */
+  float* g_a;           /* [M, d] fp32 */
+  float* g_b;           /* [M, d] fp32 */
+  void* g_T;            /* T [M, d]   */
+  void* g_h;            /* T [M, d_inner] */
+  void* g_qkv;          /* T [M, 3d]  */
+  void* g_o;            /* T [M, d]   */
+  float* dsum;          /* [B, H, Ls] */
+} me_layer_bwd_args;
+int me_layer_backward(const me_layer_bwd_args* a);
+
+/* ---------------------------------------------------------------------------------------
+ * KV-cache decode step for one layer (new capability; result must equal the reference's
+ * full-prefix recompute, generate.py:99-122, while t < max_input_len <= max_seq).
+ *   x_* [B, d] current-token activations; caches T [B, H, T_max, dh]; keypad [B, T_max].
+ *   The step writes k/v of position t into the caches, attends over keys 0..t.
+ * ------------------------------------------------------------------------------------- */
+typedef struct me_decode_layer_args {
+  me_layer_args f;  /* B, Ls = 1 ; x/out/qkv/attn_o/proj/h sized for M = B rows; keypad [B, T_max] */
+  void* k_cache;
+  void* v_cache;
+  const int32_t* t_dev; /* device int32: position of the token being processed */
+  int32_t T_max, _pad;
+} me_decode_layer_args;
+int me_decode_layer_step(const me_decode_layer_args* a);
+
+/* Copy k/v rows of a packed QKV buffer [B, Ls, 3, H, dh] (prefill) into the caches at
+ * positions pos0 .. pos0+Ls-1. */
+int me_kv_cache_write(const void* qkv, int dtype, int B, int Ls, int H, int dh, void* k_cache, void* v_cache,
+                      int T_max, int pos0, void* stream);
+
+/* Decode-step input stage: x[b,:] for token tokens[b] at position *t_dev (same arithmetic as
+ * me_embed_forward for a non-prefix position); also records keypad[b, *t_dev]. */
+int me_embed_decode(const int64_t* tokens, const float* cond, const float* emb_w, const float* cw0,
+                    const float* cb0, const float* pe, int B, int d, int d_cond, int V, int mode,
+                    int pad_token, const int32_t* t_dev, int dtype, float* x_f32, void* x_T, uint8_t* keypad,
+                    int T_max, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MIDI_EMOTION_B200_H */

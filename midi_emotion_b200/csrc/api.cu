@@ -1,0 +1,112 @@
+// Library plumbing: error text, device query, TMA descriptor construction, attention dispatch.
+#include <stdarg.h>
+#include <string.h>
+
+#include "common.cuh"
+#include "../../include/midi_emotion_b200.h"
+
+namespace me {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+int sm_count() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return 148;
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+  }
+  return n;
+}
+
+// cuTensorMapEncodeTiled through the runtime's driver entry point: the library links only cudart.
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+int make_tmap_2d_bf16(CUtensorMap* out, const void* base, uint64_t inner, uint64_t outer, uint64_t pitch_elems,
+                      uint32_t box_inner, uint32_t box_outer) {
+  EncodeTiledFn fn = encode_fn();
+  ME_CHECK(fn != nullptr, "cuTensorMapEncodeTiled entry point not available");
+  ME_CHECK(box_inner * 2 <= 128 && box_outer <= 256, "tensor map box %ux%u too large", box_inner, box_outer);
+  cuuint64_t dims[2] = {inner, outer};
+  cuuint64_t strides[1] = {pitch_elems * 2};
+  cuuint32_t box[2] = {box_inner, box_outer};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  ME_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(2d) failed: %d (inner=%llu outer=%llu pitch=%llu box=%ux%u base=%p)",
+           static_cast<int>(r), (unsigned long long)inner, (unsigned long long)outer,
+           (unsigned long long)pitch_elems, box_inner, box_outer, base);
+  return 0;
+}
+
+int make_tmap_3d_bf16(CUtensorMap* out, const void* base, uint64_t d0, uint64_t d1, uint64_t d2,
+                      uint64_t pitch1_elems, uint64_t pitch2_elems, uint32_t b0, uint32_t b1, uint32_t b2) {
+  EncodeTiledFn fn = encode_fn();
+  ME_CHECK(fn != nullptr, "cuTensorMapEncodeTiled entry point not available");
+  cuuint64_t dims[3] = {d0, d1, d2};
+  cuuint64_t strides[2] = {pitch1_elems * 2, pitch2_elems * 2};
+  cuuint32_t box[3] = {b0, b1, b2};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  ME_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(3d) failed: %d", static_cast<int>(r));
+  return 0;
+}
+
+int launch_attn_fwd_simt(const me_attn_args* a);
+int launch_attn_bwd_simt(const me_attn_bwd_args* a);
+int launch_attn_fwd_tc(const me_attn_args* a);
+int launch_attn_bwd_tc(const me_attn_bwd_args* a);
+
+}  // namespace me
+
+extern "C" const char* me_last_error(void) { return me::g_err; }
+extern "C" int me_version(void) { return 100; }
+
+extern "C" int me_device_is_sm100(void) {
+  static int cached = -1;
+  if (cached < 0) {
+    int dev = 0, major = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return 0;
+    if (cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev) != cudaSuccess) return 0;
+    cached = (major == 10) ? 1 : 0;
+  }
+  return cached;
+}
+
+extern "C" int me_attention_forward(const me_attn_args* a) {
+  using namespace me;
+  ME_CHECK(a != nullptr, "me_attention_forward: NULL args");
+  if (a->impl == ME_ATTN_TENSOR) return launch_attn_fwd_tc(a);
+  return launch_attn_fwd_simt(a);
+}
+
+extern "C" int me_attention_backward(const me_attn_bwd_args* a) {
+  using namespace me;
+  ME_CHECK(a != nullptr, "me_attention_backward: NULL args");
+  if (a->f.impl == ME_ATTN_TENSOR) return launch_attn_bwd_tc(a);
+  return launch_attn_bwd_simt(a);
+}

@@ -1,0 +1,489 @@
+// HBM-bound kernels of the hot path: input stage (embedding + conditioning + positional table),
+// residual-add + LayerNorm forward/backward, column sums, dtype conversion, KV-cache append.
+// All of them stream each byte once with 16-byte vector accesses where alignment allows.
+#include "common.cuh"
+#include "../../include/midi_emotion_b200.h"
+
+namespace me {
+
+// =====================================================================================
+// Input stage (music_multi.py:89-102, music_continuous_token.py:81-100)
+// =====================================================================================
+template <typename T>
+__global__ void embed_fwd_kernel(const int64_t* __restrict__ tokens, const float* __restrict__ cond,
+                                 const float* __restrict__ emb_w, const float* __restrict__ cw0,
+                                 const float* __restrict__ cb0, const float* __restrict__ cw1,
+                                 const float* __restrict__ cb1, const float* __restrict__ pe, int B, int L,
+                                 int d, int dc, int V, int mode, int pad_token, float p, uint64_t seed,
+                                 const int32_t* __restrict__ t_dev, int T_max, float* __restrict__ x_f32,
+                                 T* __restrict__ x_T, uint8_t* __restrict__ keypad) {
+  // one block per output row (b, s); decode mode (t_dev != NULL): L == 1, s = *t_dev
+  const bool ctoken = (mode == ME_COND_CONTINUOUS_TOKEN);
+  const int row = blockIdx.x;
+  int b, s, pos;
+  int64_t out_row;
+  if (t_dev != nullptr) {  // decode: single position per sequence, never a prefix slot
+    b = row;
+    pos = *t_dev;
+    s = ctoken ? 2 : 0;
+    out_row = b;
+  } else {
+    const int Ls = ctoken ? L + 2 : L;
+    b = row / Ls;
+    s = row - b * Ls;
+    pos = s;
+    out_row = row;
+  }
+  const int de = d - dc;
+  const float scale = sqrtf(static_cast<float>(de));
+  const float inv_keep = p > 0.f ? 1.f / (1.f - p) : 1.f;
+  int64_t tok = -1;
+  const bool prefix = ctoken && t_dev == nullptr && s < 2;
+  if (!prefix) {
+    tok = (t_dev != nullptr) ? tokens[b] : tokens[static_cast<int64_t>(b) * L + (ctoken ? s - 2 : s)];
+  }
+  if (threadIdx.x == 0 && keypad != nullptr) {
+    const uint8_t kp = (!prefix && tok == pad_token) ? 1 : 0;
+    if (t_dev != nullptr) keypad[static_cast<int64_t>(b) * T_max + pos] = kp;
+    else keypad[row] = kp;
+  }
+  const bool tok_ok = tok >= 0 && tok < V;
+  float c0 = 0.f, c1 = 0.f;
+  if (mode == ME_COND_CONTINUOUS_CONCAT || prefix) {
+    c0 = cond[b * 2 + 0];
+    c1 = cond[b * 2 + 1];
+  }
+  const float* perow = pe + static_cast<int64_t>(pos) * d;
+  for (int c = threadIdx.x; c < d; c += blockDim.x) {
+    float v;
+    if (prefix) {
+      // Linear(1, d): cond[b, s] * w[c, 0] + bias[c]
+      v = (s == 0) ? fmaf(c0, cw0[c], cb0[c]) : fmaf(c1, cw1[c], cb1[c]);
+    } else if (c < de) {
+      v = tok_ok ? emb_w[tok * de + c] * scale : 0.f;
+    } else {
+      const int j = c - de;  // Linear(2, dc)
+      v = cb0[j] + (c0 * cw0[j * 2 + 0] + c1 * cw0[j * 2 + 1]);
+    }
+    v += perow[c];
+    v *= dropout_scale(p, inv_keep, seed, static_cast<uint64_t>(out_row) * d + c);
+    x_f32[out_row * d + c] = v;
+    if (x_T != nullptr && static_cast<void*>(x_T) != static_cast<void*>(x_f32))
+      x_T[out_row * d + c] = from_f32<T>(v);
+  }
+}
+
+// dEmb[tok] += dx * sqrt(de) (pad rows skipped: Embedding(padding_idx=0) gets zero gradient);
+// fc_condition grads reduced over the sequence.  One block per (b, s) row, fp32 atomics.
+__global__ void embed_bwd_kernel(const float* __restrict__ dx, const int64_t* __restrict__ tokens,
+                                 const float* __restrict__ cond, int B, int L, int d, int dc, int V, int mode,
+                                 int pad_token, float p, uint64_t seed, float* __restrict__ d_emb,
+                                 float* __restrict__ d_cw0, float* __restrict__ d_cb0, float* __restrict__ d_cw1,
+                                 float* __restrict__ d_cb1) {
+  const bool ctoken = (mode == ME_COND_CONTINUOUS_TOKEN);
+  const int Ls = ctoken ? L + 2 : L;
+  const int row = blockIdx.x;
+  const int b = row / Ls;
+  const int s = row - b * Ls;
+  const int de = d - dc;
+  const float scale = sqrtf(static_cast<float>(de));
+  const float inv_keep = p > 0.f ? 1.f / (1.f - p) : 1.f;
+  const bool prefix = ctoken && s < 2;
+  int64_t tok = -1;
+  if (!prefix) tok = tokens[static_cast<int64_t>(b) * L + (ctoken ? s - 2 : s)];
+  float c0 = 0.f, c1 = 0.f;
+  if (mode == ME_COND_CONTINUOUS_CONCAT || prefix) {
+    c0 = cond[b * 2 + 0];
+    c1 = cond[b * 2 + 1];
+  }
+  for (int c = threadIdx.x; c < d; c += blockDim.x) {
+    float g = dx[static_cast<int64_t>(row) * d + c];
+    g *= dropout_scale(p, inv_keep, seed, static_cast<uint64_t>(row) * d + c);
+    if (prefix) {
+      if (s == 0) {
+        atomicAdd(&d_cw0[c], g * c0);
+        atomicAdd(&d_cb0[c], g);
+      } else {
+        atomicAdd(&d_cw1[c], g * c1);
+        atomicAdd(&d_cb1[c], g);
+      }
+    } else if (c < de) {
+      if (tok != pad_token && tok >= 0 && tok < V) atomicAdd(&d_emb[tok * de + c], g * scale);
+    } else {
+      const int j = c - de;
+      atomicAdd(&d_cw0[j * 2 + 0], g * c0);
+      atomicAdd(&d_cw0[j * 2 + 1], g * c1);
+      atomicAdd(&d_cb0[j], g);
+    }
+  }
+}
+
+// =====================================================================================
+// out = LayerNorm(x_res + dropout(y)),  one warp per row, row staged in shared memory
+// (music_multi.py:128-129,133-134).  Statistics two-pass in fp32 (mean, then biased variance).
+// =====================================================================================
+constexpr int LN_WARPS = 4;
+
+template <typename T>
+__global__ void add_ln_fwd_kernel(const float* __restrict__ x_res, const T* __restrict__ y,
+                                  const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
+                                  int M, int d, float p, uint64_t seed, float* __restrict__ out_f32,
+                                  T* __restrict__ out_T, float* __restrict__ zsave, float* __restrict__ mean_out,
+                                  float* __restrict__ rstd_out) {
+  extern __shared__ float ln_smem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t row = static_cast<int64_t>(blockIdx.x) * LN_WARPS + warp;
+  if (row >= M) return;
+  float* zr = ln_smem + warp * d;
+  const float inv_keep = p > 0.f ? 1.f / (1.f - p) : 1.f;
+  float sum = 0.f;
+  for (int c = lane; c < d; c += 32) {
+    const int64_t idx = row * d + c;
+    float yv = to_f32<T>(y[idx]);
+    yv *= dropout_scale(p, inv_keep, seed, static_cast<uint64_t>(idx));
+    const float z = yv + x_res[idx];
+    zr[c] = z;
+    sum += z;
+  }
+  const float mean = warp_sum(sum) / d;
+  float vs = 0.f;
+  for (int c = lane; c < d; c += 32) {
+    const float dz = zr[c] - mean;
+    vs += dz * dz;
+  }
+  const float rstd = 1.f / sqrtf(warp_sum(vs) / d + eps);
+  if (lane == 0) {
+    if (mean_out) mean_out[row] = mean;
+    if (rstd_out) rstd_out[row] = rstd;
+  }
+  const bool alias = static_cast<void*>(out_T) == static_cast<void*>(out_f32);
+  for (int c = lane; c < d; c += 32) {
+    const int64_t idx = row * d + c;
+    const float z = zr[c];
+    const float o = (z - mean) * rstd * gamma[c] + beta[c];
+    if (zsave) zsave[idx] = z;
+    out_f32[idx] = o;
+    if (out_T != nullptr && !alias) out_T[idx] = from_f32<T>(o);
+  }
+}
+
+// LayerNorm backward.  Each block owns a contiguous chunk of rows; every lane keeps the partial
+// d_gamma / d_beta sums of its own columns (c = lane + 32k) in registers across the rows its warp
+// visits, the warps combine through shared memory and flush one atomicAdd per column per block.
+template <typename T, int KMAX>
+__global__ void add_ln_bwd_kernel(const float* __restrict__ dout, const float* __restrict__ dout_add,
+                                  const float* __restrict__ z, const float* __restrict__ mean,
+                                  const float* __restrict__ rstd, const float* __restrict__ gamma, int M, int d,
+                                  int rows_per_block, float p, uint64_t seed, float* __restrict__ dz_f32,
+                                  T* __restrict__ dy_T, float* __restrict__ d_gamma,
+                                  float* __restrict__ d_beta) {
+  extern __shared__ float ln_smem[];
+  float* dg_s = ln_smem;        // [d]
+  float* db_s = ln_smem + d;    // [d]
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int c = threadIdx.x; c < d; c += blockDim.x) {
+    dg_s[c] = 0.f;
+    db_s[c] = 0.f;
+  }
+  __syncthreads();
+  float dg[KMAX], db[KMAX], gam[KMAX];
+#pragma unroll
+  for (int k = 0; k < KMAX; ++k) {
+    dg[k] = 0.f;
+    db[k] = 0.f;
+    const int c = lane + 32 * k;
+    gam[k] = c < d ? gamma[c] : 0.f;
+  }
+  const float inv_keep = p > 0.f ? 1.f / (1.f - p) : 1.f;
+  const int64_t r0 = static_cast<int64_t>(blockIdx.x) * rows_per_block;
+  const int64_t r1 = min(static_cast<int64_t>(M), r0 + rows_per_block);
+  const bool alias = static_cast<void*>(dy_T) == static_cast<void*>(dz_f32);
+  for (int64_t row = r0 + warp; row < r1; row += LN_WARPS) {
+    const float mu = mean[row], rs = rstd[row];
+    float dyv[KMAX], xh[KMAX];
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int k = 0; k < KMAX; ++k) {
+      const int c = lane + 32 * k;
+      dyv[k] = 0.f;
+      xh[k] = 0.f;
+      if (c < d) {
+        const int64_t idx = row * d + c;
+        float dy = dout[idx];
+        if (dout_add) dy += dout_add[idx];
+        dyv[k] = dy;
+        xh[k] = (z[idx] - mu) * rs;
+        const float g = dy * gam[k];
+        s1 += g;
+        s2 += g * xh[k];
+        dg[k] += dy * xh[k];
+        db[k] += dy;
+      }
+    }
+    s1 = warp_sum(s1) / d;
+    s2 = warp_sum(s2) / d;
+#pragma unroll
+    for (int k = 0; k < KMAX; ++k) {
+      const int c = lane + 32 * k;
+      if (c < d) {
+        const int64_t idx = row * d + c;
+        const float dzv = rs * (dyv[k] * gam[k] - s1 - xh[k] * s2);
+        if (dz_f32) dz_f32[idx] = dzv;
+        if (dy_T != nullptr && !alias)
+          dy_T[idx] = from_f32<T>(dzv * dropout_scale(p, inv_keep, seed, static_cast<uint64_t>(idx)));
+      }
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < KMAX; ++k) {
+    const int c = lane + 32 * k;
+    if (c < d) {
+      atomicAdd(&dg_s[c], dg[k]);
+      atomicAdd(&db_s[c], db[k]);
+    }
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < d; c += blockDim.x) {
+    atomicAdd(&d_gamma[c], dg_s[c]);
+    atomicAdd(&d_beta[c], db_s[c]);
+  }
+}
+
+// =====================================================================================
+// column sums (bias gradients)
+// =====================================================================================
+template <typename T>
+__global__ void colsum_kernel(const T* __restrict__ X, int M, int N, int ldx, int rows_per_block,
+                              float* __restrict__ out) {
+  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= N) return;
+  const int64_t r0 = static_cast<int64_t>(blockIdx.y) * rows_per_block;
+  const int64_t r1 = min(static_cast<int64_t>(M), r0 + rows_per_block);
+  float acc = 0.f;
+  for (int64_t r = r0; r < r1; ++r) acc += to_f32<T>(X[r * ldx + n]);
+  atomicAdd(&out[n], acc);
+}
+
+template <typename TS, typename TD>
+__global__ void convert2d_kernel(const TS* __restrict__ src, int ld_src, TD* __restrict__ dst, int ld_dst,
+                                 int rows, int cols) {
+  const int64_t total = static_cast<int64_t>(rows) * ld_dst;
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int64_t r = i / ld_dst;
+    const int c = static_cast<int>(i - r * ld_dst);
+    dst[i] = from_f32<TD>(c < cols ? to_f32<TS>(src[r * ld_src + c]) : 0.f);
+  }
+}
+
+// =====================================================================================
+// KV cache append: rows of a packed QKV buffer -> [B, H, T_max, dh] caches
+// =====================================================================================
+template <typename T>
+__global__ void kv_write_kernel(const T* __restrict__ qkv, int B, int Ls, int H, int dh, T* __restrict__ kc,
+                                T* __restrict__ vc, int T_max, int pos0, const int32_t* __restrict__ t_dev) {
+  const int d = H * dh;
+  const int64_t total = static_cast<int64_t>(B) * Ls * d;
+  const int p0 = t_dev ? *t_dev : pos0;
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int c = static_cast<int>(i % d);
+    const int64_t row = i / d;
+    const int s = static_cast<int>(row % Ls);
+    const int b = static_cast<int>(row / Ls);
+    const int h = c / dh, e = c - h * dh;
+    const int64_t dst = ((static_cast<int64_t>(b) * H + h) * T_max + (p0 + s)) * dh + e;
+    kc[dst] = qkv[row * 3 * d + d + c];
+    vc[dst] = qkv[row * 3 * d + 2 * d + c];
+  }
+}
+
+int launch_kv_write(const void* qkv, int dtype, int B, int Ls, int H, int dh, void* kc, void* vc, int T_max,
+                    int pos0, const int32_t* t_dev, cudaStream_t st) {
+  const int64_t total = static_cast<int64_t>(B) * Ls * H * dh;
+  const int64_t want = (total + 255) / 256;
+  const int blocks = static_cast<int>(want < 148 * 8 ? want : 148 * 8);
+  if (dtype == ME_BF16)
+    kv_write_kernel<bf16><<<blocks, 256, 0, st>>>(static_cast<const bf16*>(qkv), B, Ls, H, dh,
+                                                  static_cast<bf16*>(kc), static_cast<bf16*>(vc), T_max, pos0, t_dev);
+  else
+    kv_write_kernel<float><<<blocks, 256, 0, st>>>(static_cast<const float*>(qkv), B, Ls, H, dh,
+                                                   static_cast<float*>(kc), static_cast<float*>(vc), T_max, pos0,
+                                                   t_dev);
+  ME_LAUNCH_CHECK();
+  return 0;
+}
+
+int launch_embed(const int64_t* tokens, const float* cond, const float* emb_w, const float* cw0,
+                 const float* cb0, const float* cw1, const float* cb1, const float* pe, int B, int L, int d,
+                 int d_cond, int V, int mode, int pad_token, float p, uint64_t seed, const int32_t* t_dev,
+                 int T_max, int dtype, float* x_f32, void* x_T, uint8_t* keypad, cudaStream_t st) {
+  const int Ls = (mode == ME_COND_CONTINUOUS_TOKEN && t_dev == nullptr) ? L + 2 : L;
+  const int rows = B * Ls;
+  const int threads = d >= 512 ? 256 : 128;
+  if (dtype == ME_BF16)
+    embed_fwd_kernel<bf16><<<rows, threads, 0, st>>>(tokens, cond, emb_w, cw0, cb0, cw1, cb1, pe, B, L, d, d_cond,
+                                                     V, mode, pad_token, p, seed, t_dev, T_max, x_f32,
+                                                     static_cast<bf16*>(x_T), keypad);
+  else
+    embed_fwd_kernel<float><<<rows, threads, 0, st>>>(tokens, cond, emb_w, cw0, cb0, cw1, cb1, pe, B, L, d,
+                                                      d_cond, V, mode, pad_token, p, seed, t_dev, T_max, x_f32,
+                                                      static_cast<float*>(x_T), keypad);
+  ME_LAUNCH_CHECK();
+  return 0;
+}
+
+int launch_add_ln_fwd(const float* x_res, const void* y, int dtype, const float* gamma, const float* beta,
+                      float eps, int M, int d, float p, uint64_t seed, float* out_f32, void* out_T, float* z,
+                      float* mean, float* rstd, cudaStream_t st) {
+  const int blocks = (M + LN_WARPS - 1) / LN_WARPS;
+  const size_t smem = static_cast<size_t>(LN_WARPS) * d * sizeof(float);
+  if (dtype == ME_BF16)
+    add_ln_fwd_kernel<bf16><<<blocks, LN_WARPS * 32, smem, st>>>(x_res, static_cast<const bf16*>(y), gamma, beta,
+                                                                 eps, M, d, p, seed, out_f32,
+                                                                 static_cast<bf16*>(out_T), z, mean, rstd);
+  else
+    add_ln_fwd_kernel<float><<<blocks, LN_WARPS * 32, smem, st>>>(x_res, static_cast<const float*>(y), gamma, beta,
+                                                                  eps, M, d, p, seed, out_f32,
+                                                                  static_cast<float*>(out_T), z, mean, rstd);
+  ME_LAUNCH_CHECK();
+  return 0;
+}
+
+int launch_add_ln_bwd(const float* dout, const float* dout_add, const float* z, const float* mean,
+                      const float* rstd, const float* gamma, int M, int d, float p, uint64_t seed, int dtype,
+                      float* dz_f32, void* dy_T, float* d_gamma, float* d_beta, cudaStream_t st) {
+  int blocks = sm_count() * 4;
+  int rpb = (M + blocks - 1) / blocks;
+  rpb = ((rpb + LN_WARPS - 1) / LN_WARPS) * LN_WARPS;
+  if (rpb < LN_WARPS) rpb = LN_WARPS;
+  blocks = (M + rpb - 1) / rpb;
+  const size_t smem = 2 * static_cast<size_t>(d) * sizeof(float);
+#define ME_LN_BWD(KM)                                                                                          \
+  do {                                                                                                         \
+    if (dtype == ME_BF16)                                                                                      \
+      add_ln_bwd_kernel<bf16, KM><<<blocks, LN_WARPS * 32, smem, st>>>(dout, dout_add, z, mean, rstd, gamma, M, \
+                                                                       d, rpb, p, seed, dz_f32,                \
+                                                                       static_cast<bf16*>(dy_T), d_gamma, d_beta); \
+    else                                                                                                       \
+      add_ln_bwd_kernel<float, KM><<<blocks, LN_WARPS * 32, smem, st>>>(dout, dout_add, z, mean, rstd, gamma, M, \
+                                                                        d, rpb, p, seed, dz_f32,               \
+                                                                        static_cast<float*>(dy_T), d_gamma, d_beta); \
+  } while (0)
+  if (d <= 128) ME_LN_BWD(4);
+  else if (d <= 256) ME_LN_BWD(8);
+  else if (d <= 512) ME_LN_BWD(16);
+  else if (d <= 768) ME_LN_BWD(24);
+  else if (d <= 1024) ME_LN_BWD(32);
+  else if (d <= 2048) ME_LN_BWD(64);
+  else { set_error("layernorm backward: d=%d > 2048 unsupported", d); return 1; }
+#undef ME_LN_BWD
+  ME_LAUNCH_CHECK();
+  return 0;
+}
+
+int launch_colsum(const void* X, int dtype, int M, int N, int ldx, float* out, cudaStream_t st) {
+  const int threads = 128;
+  const int gx = (N + threads - 1) / threads;
+  int gy = max(1, (sm_count() * 4) / gx);
+  int rpb = (M + gy - 1) / gy;
+  if (rpb < 32) rpb = 32;
+  gy = (M + rpb - 1) / rpb;
+  dim3 grid(gx, gy);
+  if (dtype == ME_BF16)
+    colsum_kernel<bf16><<<grid, threads, 0, st>>>(static_cast<const bf16*>(X), M, N, ldx, rpb, out);
+  else
+    colsum_kernel<float><<<grid, threads, 0, st>>>(static_cast<const float*>(X), M, N, ldx, rpb, out);
+  ME_LAUNCH_CHECK();
+  return 0;
+}
+
+}  // namespace me
+
+using namespace me;
+
+extern "C" int me_embed_forward(const int64_t* tokens, const float* cond, const float* emb_w, const float* cw0,
+                                const float* cb0, const float* cw1, const float* cb1, const float* pe, int B,
+                                int L, int d, int d_cond, int V, int mode, int pad_token, float dropout_p,
+                                uint64_t seed, int dtype, float* x_f32, void* x_T, uint8_t* keypad, void* stream) {
+  ME_CHECK(B > 0 && L > 0 && d > 0 && d_cond >= 0 && d_cond < d, "me_embed_forward: bad dims");
+  ME_CHECK(mode >= 0 && mode <= 3, "me_embed_forward: bad mode %d", mode);
+  ME_CHECK(mode == ME_COND_CONTINUOUS_CONCAT || d_cond == 0, "me_embed_forward: d_cond>0 needs concat mode");
+  const int Ls = mode == ME_COND_CONTINUOUS_TOKEN ? L + 2 : L;
+  ME_CHECK(Ls <= 2048, "me_embed_forward: sequence length %d exceeds max_seq", Ls);
+  return launch_embed(tokens, cond, emb_w, cw0, cb0, cw1, cb1, pe, B, L, d, d_cond, V, mode, pad_token,
+                      dropout_p, seed, nullptr, 0, dtype, x_f32, x_T, keypad, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int me_embed_decode(const int64_t* tokens, const float* cond, const float* emb_w, const float* cw0,
+                               const float* cb0, const float* pe, int B, int d, int d_cond, int V, int mode,
+                               int pad_token, const int32_t* t_dev, int dtype, float* x_f32, void* x_T,
+                               uint8_t* keypad, int T_max, void* stream) {
+  ME_CHECK(t_dev != nullptr, "me_embed_decode: t_dev is NULL");
+  return launch_embed(tokens, cond, emb_w, cw0, cb0, nullptr, nullptr, pe, B, 1, d, d_cond, V, mode, pad_token,
+                      0.f, 0, t_dev, T_max, dtype, x_f32, x_T, keypad, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int me_embed_backward(const float* dx, const int64_t* tokens, const float* cond, int B, int L, int d,
+                                 int d_cond, int V, int mode, int pad_token, float dropout_p, uint64_t seed,
+                                 float* d_emb, float* d_cw0, float* d_cb0, float* d_cw1, float* d_cb1,
+                                 void* stream) {
+  const int Ls = mode == ME_COND_CONTINUOUS_TOKEN ? L + 2 : L;
+  const int threads = d >= 512 ? 256 : 128;
+  embed_bwd_kernel<<<B * Ls, threads, 0, static_cast<cudaStream_t>(stream)>>>(
+      dx, tokens, cond, B, L, d, d_cond, V, mode, pad_token, dropout_p, seed, d_emb, d_cw0, d_cb0, d_cw1, d_cb1);
+  ME_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int me_add_layernorm_forward(const float* x_res, const void* y, int dtype, const float* gamma,
+                                        const float* beta, float eps, int M, int d, float dropout_p,
+                                        uint64_t seed, float* out_f32, void* out_T, float* z, float* mean,
+                                        float* rstd, void* stream) {
+  ME_CHECK(M > 0 && d > 0 && d <= 8192, "me_add_layernorm_forward: bad dims M=%d d=%d", M, d);
+  return launch_add_ln_fwd(x_res, y, dtype, gamma, beta, eps, M, d, dropout_p, seed, out_f32, out_T, z, mean,
+                           rstd, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int me_add_layernorm_backward(const float* dout, const float* dout_add, const float* z,
+                                         const float* mean, const float* rstd, const float* gamma, int M, int d,
+                                         float dropout_p, uint64_t seed, int dtype, float* dz_f32, void* dy_T,
+                                         float* d_gamma, float* d_beta, void* stream) {
+  ME_CHECK(M > 0 && d > 0 && d <= 2048, "me_add_layernorm_backward: bad dims");
+  return launch_add_ln_bwd(dout, dout_add, z, mean, rstd, gamma, M, d, dropout_p, seed, dtype, dz_f32, dy_T,
+                           d_gamma, d_beta, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int me_colsum(const void* X, int dtype, int M, int N, int ldx, float* out, void* stream) {
+  return launch_colsum(X, dtype, M, N, ldx, out, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int me_convert_2d(const void* src, int src_dtype, int ld_src, void* dst, int dst_dtype, int ld_dst,
+                             int rows, int cols, void* stream) {
+  const int64_t total = static_cast<int64_t>(rows) * ld_dst;
+  const int64_t want = (total + 255) / 256;
+  const int blocks = static_cast<int>(want < 148 * 16 ? want : 148 * 16);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (src_dtype == ME_F32 && dst_dtype == ME_BF16)
+    convert2d_kernel<float, bf16><<<blocks, 256, 0, st>>>(static_cast<const float*>(src), ld_src,
+                                                          static_cast<bf16*>(dst), ld_dst, rows, cols);
+  else if (src_dtype == ME_BF16 && dst_dtype == ME_F32)
+    convert2d_kernel<bf16, float><<<blocks, 256, 0, st>>>(static_cast<const bf16*>(src), ld_src,
+                                                          static_cast<float*>(dst), ld_dst, rows, cols);
+  else if (src_dtype == ME_F32 && dst_dtype == ME_F32)
+    convert2d_kernel<float, float><<<blocks, 256, 0, st>>>(static_cast<const float*>(src), ld_src,
+                                                           static_cast<float*>(dst), ld_dst, rows, cols);
+  else
+    convert2d_kernel<bf16, bf16><<<blocks, 256, 0, st>>>(static_cast<const bf16*>(src), ld_src,
+                                                         static_cast<bf16*>(dst), ld_dst, rows, cols);
+  ME_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int me_kv_cache_write(const void* qkv, int dtype, int B, int Ls, int H, int dh, void* k_cache,
+                                 void* v_cache, int T_max, int pos0, void* stream) {
+  ME_CHECK(pos0 >= 0 && pos0 + Ls <= T_max, "me_kv_cache_write: positions %d..%d exceed T_max %d", pos0,
+           pos0 + Ls, T_max);
+  return launch_kv_write(qkv, dtype, B, Ls, H, dh, k_cache, v_cache, T_max, pos0, nullptr,
+                         static_cast<cudaStream_t>(stream));
+}
