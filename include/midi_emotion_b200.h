@@ -43,8 +43,16 @@ extern "C" {
 
 const char* me_last_error(void);
 int me_version(void);
+/* number of CUDA kernels this library has launched in this process (benchmark bookkeeping) */
+unsigned long long me_launch_count(void);
 /* 1 when the running device is sm_100 (B200); the tcgen05 paths refuse to run otherwise. */
 int me_device_is_sm100(void);
+/* sizeof() of the argument structs below, for binding self-checks (ctypes/cgo/JNI mirrors). */
+int me_sizeof_attn_args(void);
+int me_sizeof_attn_bwd_args(void);
+int me_sizeof_layer_args(void);
+int me_sizeof_layer_bwd_args(void);
+int me_sizeof_decode_layer_args(void);
 
 /* ---------------------------------------------------------------------------------------
  * Input stage.  Replaces models/music_multi.py:89-102 (generate_mask, Embedding, *sqrt(d-dc),
@@ -80,6 +88,14 @@ int me_embed_backward(const float* dx, const int64_t* tokens, const float* cond,
 int me_gemm_bf16(const void* A, const void* B, void* D, int M, int N, int K, int lda, int ldb, int ldd,
                  int a_mn, int b_mn, int out_dtype, int epi_flags, const float* bias, const float* addend,
                  const void* relu_mask, int ldmask, void* stream);
+/* tuning/test hook: same as me_gemm_bf16 with a forced tile width (32/64/128/256, 0 = auto) and
+ * split-K factor (0 = auto). */
+int me_gemm_bf16_ex(const void* A, const void* B, void* D, int M, int N, int K, int lda, int ldb, int ldd,
+                    int a_mn, int b_mn, int out_dtype, int epi_flags, const float* bias, const float* addend,
+                    const void* relu_mask, int ldmask, int tile_n, int splits, void* stream);
+/* test hook: fp32 D = bf16 A . bf16 B^T on CUDA cores (device-side reference for the tcgen05 GEMM). */
+int me_gemm_bf16_reference(const void* A, const void* B, float* D, int M, int N, int K, int lda, int ldb,
+                           int ldd, int a_mn, int b_mn, void* stream);
 int me_gemm_f32(const float* A, const float* B, float* D, int M, int N, int K, int lda, int ldb, int ldd,
                 int a_mn, int b_mn, int epi_flags, const float* bias, const float* addend,
                 const float* relu_mask, int ldmask, void* stream);

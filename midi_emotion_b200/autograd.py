@@ -1,0 +1,253 @@
+"""Whole-model forward / backward over the C-ABI, exposed to PyTorch as one autograd.Function.
+
+Forward replaces MusicTransformerMulti.forward / MusicTransformerContinuousToken.forward
+(models/music_multi.py:84-108, models/music_continuous_token.py:77-105); backward replaces the
+autograd graph that train.py:317 walks.  PyTorch only owns memory and streams here.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import List, Optional
+
+import torch
+
+from . import _lib
+from ._lib import ME_BF16, ME_F32, ptr
+
+_SEED_MASK = (1 << 40) - 1
+
+
+def _tdtype(dtype: int):
+    return torch.bfloat16 if dtype == ME_BF16 else torch.float32
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+class _Acts:
+    """Activations of one forward pass (kept alive for backward when grad is needed)."""
+    __slots__ = ("dtype", "B", "L", "Ls", "M", "x_f32", "x_T", "keypad", "layers", "seed", "training", "p",
+                 "attn_impl", "Vp")
+
+
+def _layer_args(model, wl: dict, lay, act: dict, x_f32, x_T, keypad, a: _Acts, layer_idx: int) -> _lib.LayerArgs:
+    la = _lib.LayerArgs()
+    la.dtype, la.attn_impl, la.training = a.dtype, a.attn_impl, 1 if a.training else 0
+    la.B, la.Ls, la.d, la.H = a.B, a.Ls, model.embedding_dim, model.num_head
+    la.d_inner, la.max_seq = model.d_inner, model.max_seq
+    la.dropout_p, la.ln_eps = a.p, 1e-6
+    la.seed = ((a.seed << 8) + layer_idx) & ((1 << 62) - 1)
+    la.x_f32, la.x_T, la.keypad = ptr(x_f32), ptr(x_T), ptr(keypad)
+    la.Wqkv, la.bqkv, la.E, la.Wo = ptr(wl["Wqkv"]), ptr(wl["bqkv"]), ptr(wl["E"]), ptr(wl["Wo"])
+    la.bo = ptr(lay.rga.fc.bias)
+    la.ln1_w, la.ln1_b = ptr(lay.layernorm1.weight), ptr(lay.layernorm1.bias)
+    la.W1, la.b1, la.W2, la.b2 = ptr(wl["W1"]), ptr(lay.FFN_pre.bias), ptr(wl["W2"]), ptr(lay.FFN_suf.bias)
+    la.ln2_w, la.ln2_b = ptr(lay.layernorm2.weight), ptr(lay.layernorm2.bias)
+    for k in ("qkv", "attn_o", "lse", "proj", "z1", "mean1", "rstd1", "out1_f32", "out1_T", "h", "z2", "mean2",
+              "rstd2", "out2_f32", "out2_T"):
+        setattr(la, k, ptr(act.get(k)))
+    la.stream = _stream()
+    return la
+
+
+def run_forward(model, tokens: torch.Tensor, cond: Optional[torch.Tensor], need_grad: bool):
+    """Enqueue the forward pass.  Returns (logits_padded [M, Vp] in compute type, acts)."""
+    dtype = model._resolve_dtype()
+    tdt = _tdtype(dtype)
+    dev = tokens.device
+    B, L = tokens.shape
+    d, di, H, V = model.embedding_dim, model.d_inner, model.num_head, model.vocab_size
+    Ls = L + 2 if model.continuous_token else L
+    if Ls > model.max_seq:
+        raise RuntimeError(f"midi_emotion_b200: sequence length {Ls} exceeds max_seq {model.max_seq}")
+    M = B * Ls
+    wc = model._weights(dtype)
+    stream = _stream()
+    a = _Acts()
+    a.dtype, a.B, a.L, a.Ls, a.M = dtype, B, L, Ls, M
+    a.training = bool(model.training and model.dropout_p > 0.0)
+    a.p = float(model.dropout_p) if a.training else 0.0
+    a.attn_impl = model._resolve_attn(dtype)
+    model._step += 1
+    a.seed = (int(torch.initial_seed()) * 1000003 + model._step) & _SEED_MASK if a.training else 0
+    f32 = dict(device=dev, dtype=torch.float32)
+    tt = dict(device=dev, dtype=tdt)
+
+    a.x_f32 = torch.empty(M, d, **f32)
+    a.x_T = a.x_f32 if dtype == ME_F32 else torch.empty(M, d, **tt)
+    a.keypad = torch.empty(B, Ls, device=dev, dtype=torch.uint8)
+    cw0, cb0, cw1, cb1 = model._cond_params()
+    _lib.call("me_embed_forward", ptr(tokens), ptr(cond), ptr(model.embedding.weight), ptr(cw0), ptr(cb0), ptr(cw1),
+              ptr(cb1), ptr(model._pe(dev)), B, L, d, model.d_condition, V, model.mode, model.pad_token, a.p,
+              a.seed << 8 | 0xFF, dtype, ptr(a.x_f32), ptr(a.x_T), ptr(a.keypad), stream)
+
+    a.layers = []
+    x_f32, x_T = a.x_f32, a.x_T
+    scratch = None
+    for l, lay in enumerate(model.enc_layers):
+        if need_grad or scratch is None:
+            act = {
+                "qkv": torch.empty(M, 3 * d, **tt), "attn_o": torch.empty(M, d, **tt),
+                "lse": torch.empty(B, H, Ls, **f32), "proj": torch.empty(M, d, **tt),
+                "h": torch.empty(M, di, **tt),
+            }
+            if need_grad:
+                act.update(z1=torch.empty(M, d, **f32), mean1=torch.empty(M, **f32), rstd1=torch.empty(M, **f32),
+                           z2=torch.empty(M, d, **f32), mean2=torch.empty(M, **f32), rstd2=torch.empty(M, **f32))
+            scratch = act
+        else:
+            act = dict(scratch)  # inference: reuse the big buffers layer after layer
+        act["out1_f32"] = torch.empty(M, d, **f32)
+        act["out1_T"] = act["out1_f32"] if dtype == ME_F32 else torch.empty(M, d, **tt)
+        act["out2_f32"] = torch.empty(M, d, **f32)
+        act["out2_T"] = act["out2_f32"] if dtype == ME_F32 else torch.empty(M, d, **tt)
+        act["x_f32"], act["x_T"] = x_f32, x_T
+        la = _layer_args(model, wc["layers"][l], lay, act, x_f32, x_T, a.keypad, a, l)
+        if need_grad:
+            la.training = 1  # keep the statistics needed by backward even when dropout is off
+            la.dropout_p = a.p
+        _lib.call("me_layer_forward", C.byref(la))
+        x_f32, x_T = act["out2_f32"], act["out2_T"]
+        if need_grad:
+            act.pop("proj", None)
+            a.layers.append(act)
+    if not need_grad:
+        a.layers.append({"out2_T": x_T, "out2_f32": x_f32})
+
+    # output head (music_multi.py:106): logits[M, V]; rows padded to Vp so that they stay 16-byte aligned
+    Vp = (V + 7) // 8 * 8
+    a.Vp = Vp
+    logits = torch.empty(M, Vp, **tt)
+    if Vp != V:
+        logits[:, V:].zero_()
+    if dtype == ME_BF16:
+        _lib.call("me_gemm_bf16", ptr(x_T), ptr(wc["Wfc"]), ptr(logits), M, V, d, d, d, Vp, 0, 0, ME_BF16,
+                  _lib.EPI_BIAS, ptr(model.fc.bias), None, None, 0, stream)
+    else:
+        _lib.call("me_gemm_f32", ptr(x_T), ptr(wc["Wfc"]), ptr(logits), M, V, d, d, d, Vp, 0, 0, _lib.EPI_BIAS,
+                  ptr(model.fc.bias), None, None, 0, stream)
+    return logits, a
+
+
+def run_backward(model, tokens, cond, a: _Acts, g_logits: torch.Tensor) -> List[Optional[torch.Tensor]]:
+    """g_logits: [M, Vp] in the compute type (pad columns zero).  Returns gradients in
+    named_parameters() order."""
+    dtype = a.dtype
+    tdt = _tdtype(dtype)
+    dev = tokens.device
+    B, L, Ls, M = a.B, a.L, a.Ls, a.M
+    d, di, H, V, Vp = model.embedding_dim, model.d_inner, model.num_head, model.vocab_size, a.Vp
+    dh = d // H
+    wc = model._weights(dtype)
+    stream = _stream()
+    f32 = dict(device=dev, dtype=torch.float32)
+    tt = dict(device=dev, dtype=tdt)
+    grads = {}
+
+    last = a.layers[-1]
+    # head: dW = g^T x, db = colsum(g), dx = g W
+    grads["fc.weight"] = torch.empty(V, d, **f32)
+    grads["fc.bias"] = torch.zeros(V, **f32)
+    d_x = torch.empty(M, d, **f32)
+    _lib.call("me_colsum", ptr(g_logits), dtype, M, V, Vp, ptr(grads["fc.bias"]), stream)
+    if dtype == ME_BF16:
+        _lib.call("me_gemm_bf16", ptr(g_logits), ptr(last["out2_T"]), ptr(grads["fc.weight"]), V, d, M, Vp, d, d, 1, 1,
+                  ME_F32, 0, None, None, None, 0, stream)
+        _lib.call("me_gemm_bf16", ptr(g_logits), ptr(wc["Wfc"]), ptr(d_x), M, d, V, Vp, d, d, 0, 1, ME_F32, 0, None,
+                  None, None, 0, stream)
+    else:
+        _lib.call("me_gemm_f32", ptr(g_logits), ptr(last["out2_T"]), ptr(grads["fc.weight"]), V, d, M, Vp, d, d, 1, 1,
+                  0, None, None, None, 0, stream)
+        _lib.call("me_gemm_f32", ptr(g_logits), ptr(wc["Wfc"]), ptr(d_x), M, d, V, Vp, d, d, 0, 1, 0, None, None,
+                  None, 0, stream)
+
+    ws = {
+        "g_a": torch.empty(M, d, **f32), "g_b": torch.empty(M, d, **f32), "g_T": torch.empty(M, d, **tt),
+        "g_h": torch.empty(M, di, **tt), "g_qkv": torch.empty(M, 3 * d, **tt), "g_o": torch.empty(M, d, **tt),
+        "dsum": torch.empty(B, H, Ls, **f32), "proj": torch.empty(M, d, **tt),
+    }
+    for l in range(model.num_layer - 1, -1, -1):
+        lay = model.enc_layers[l]
+        act = a.layers[l]
+        act["proj"] = ws["proj"]
+        pre = f"enc_layers.{l}."
+        dWqkv = torch.empty(3 * d, d, **f32)
+        dbqkv = torch.empty(3 * d, **f32)
+        g = {
+            "dWqkv": dWqkv, "dbqkv": dbqkv, "dE": torch.empty(model.max_seq, dh, **f32),
+            "dWo": torch.empty(d, d, **f32), "dbo": torch.empty(d, **f32),
+            "dln1_w": torch.empty(d, **f32), "dln1_b": torch.empty(d, **f32),
+            "dW1": torch.empty(di, d, **f32), "db1": torch.empty(di, **f32),
+            "dW2": torch.empty(d, di, **f32), "db2": torch.empty(d, **f32),
+            "dln2_w": torch.empty(d, **f32), "dln2_b": torch.empty(d, **f32),
+        }
+        ba = _lib.LayerBwdArgs()
+        ba.f = _layer_args(model, wc["layers"][l], lay, act, act["x_f32"], act["x_T"], a.keypad, a, l)
+        ba.f.training = 1
+        ba.d_out, ba.d_x = ptr(d_x), ptr(d_x)
+        for k, t in g.items():
+            setattr(ba, k, ptr(t))
+        for k in ("g_a", "g_b", "g_T", "g_h", "g_qkv", "g_o", "dsum"):
+            setattr(ba, k, ptr(ws[k]))
+        _lib.call("me_layer_backward", C.byref(ba))
+        for i, n in enumerate(("Wq", "Wk", "Wv")):
+            grads[pre + f"rga.{n}.weight"] = dWqkv[i * d:(i + 1) * d]
+            grads[pre + f"rga.{n}.bias"] = dbqkv[i * d:(i + 1) * d]
+        grads[pre + "rga.E"] = g["dE"]
+        grads[pre + "rga.fc.weight"], grads[pre + "rga.fc.bias"] = g["dWo"], g["dbo"]
+        grads[pre + "FFN_pre.weight"], grads[pre + "FFN_pre.bias"] = g["dW1"], g["db1"]
+        grads[pre + "FFN_suf.weight"], grads[pre + "FFN_suf.bias"] = g["dW2"], g["db2"]
+        grads[pre + "layernorm1.weight"], grads[pre + "layernorm1.bias"] = g["dln1_w"], g["dln1_b"]
+        grads[pre + "layernorm2.weight"], grads[pre + "layernorm2.bias"] = g["dln2_w"], g["dln2_b"]
+        a.layers[l] = None  # free this layer's activations as soon as they are consumed
+
+    # input stage
+    d_emb = torch.zeros_like(model.embedding.weight)
+    grads["embedding.weight"] = d_emb
+    cw0, cb0, cw1, cb1 = model._cond_params()
+    d_c = [torch.zeros_like(t) if t is not None else None for t in (cw0, cb0, cw1, cb1)]
+    _lib.call("me_embed_backward", ptr(d_x), ptr(tokens), ptr(cond), B, L, d, model.d_condition, V, model.mode,
+              model.pad_token, a.p, a.seed << 8 | 0xFF, ptr(d_emb), ptr(d_c[0]), ptr(d_c[1]), ptr(d_c[2]),
+              ptr(d_c[3]), stream)
+    if model.continuous_token:
+        grads["fc_condition.0.weight"], grads["fc_condition.0.bias"] = d_c[0], d_c[1]
+        grads["fc_condition.1.weight"], grads["fc_condition.1.bias"] = d_c[2], d_c[3]
+    elif model.d_condition > 0:
+        grads["fc_condition.weight"], grads["fc_condition.bias"] = d_c[0], d_c[1]
+    return [grads[n] for n, _ in model.named_parameters()]
+
+
+class _ModelFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, model, tokens, cond, need_grad, *params):
+        logits_p, acts = run_forward(model, tokens, cond, need_grad)
+        ctx.model, ctx.tokens, ctx.cond, ctx.acts = model, tokens, cond, acts
+        ctx.n_params = len(params)
+        V = model.vocab_size
+        out = logits_p.view(acts.B, acts.Ls, acts.Vp)
+        return out[:, :, :V] if acts.Vp != V else out
+
+    @staticmethod
+    def backward(ctx, g_out):
+        model, a = ctx.model, ctx.acts
+        if a.layers is None or len(a.layers) != model.num_layer or a.layers[0] is None or "z1" not in a.layers[0]:
+            raise RuntimeError("midi_emotion_b200: backward called twice or forward ran without grad")
+        V, Vp, M = model.vocab_size, a.Vp, a.M
+        tdt = _tdtype(a.dtype)
+        src_dt = {torch.float32: ME_F32, torch.bfloat16: ME_BF16}.get(g_out.dtype)
+        if src_dt is None:
+            g_out = g_out.float()
+            src_dt = ME_F32
+        g_out = g_out.contiguous()
+        g_logits = torch.empty(M, Vp, device=g_out.device, dtype=tdt)
+        _lib.call("me_convert_2d", ptr(g_out), src_dt, V, ptr(g_logits), a.dtype, Vp, M, V, _stream())
+        grads = run_backward(model, ctx.tokens, ctx.cond, a, g_logits)
+        ctx.acts = None
+        return (None, None, None, None, *grads)
+
+
+def model_apply(model, tokens, cond):
+    params = model._param_list()
+    need_grad = torch.is_grad_enabled() and any(p.requires_grad for p in params)
+    return _ModelFn.apply(model, tokens, cond, need_grad, *params)

@@ -8,6 +8,7 @@
 namespace me {
 
 static thread_local char g_err[512] = "";
+unsigned long long g_launch_count = 0;
 
 void set_error(const char* fmt, ...) {
   va_list ap;
@@ -85,6 +86,7 @@ int launch_attn_bwd_tc(const me_attn_bwd_args* a);
 
 extern "C" const char* me_last_error(void) { return me::g_err; }
 extern "C" int me_version(void) { return 100; }
+extern "C" unsigned long long me_launch_count(void) { return me::g_launch_count; }
 
 extern "C" int me_device_is_sm100(void) {
   static int cached = -1;
@@ -110,3 +112,10 @@ extern "C" int me_attention_backward(const me_attn_bwd_args* a) {
   if (a->f.impl == ME_ATTN_TENSOR) return launch_attn_bwd_tc(a);
   return launch_attn_bwd_simt(a);
 }
+
+// Binding self-check: hosts mirror the argument structs (ctypes / cgo / JNI) and compare sizes at load.
+extern "C" int me_sizeof_attn_args(void) { return static_cast<int>(sizeof(me_attn_args)); }
+extern "C" int me_sizeof_attn_bwd_args(void) { return static_cast<int>(sizeof(me_attn_bwd_args)); }
+extern "C" int me_sizeof_layer_args(void) { return static_cast<int>(sizeof(me_layer_args)); }
+extern "C" int me_sizeof_layer_bwd_args(void) { return static_cast<int>(sizeof(me_layer_bwd_args)); }
+extern "C" int me_sizeof_decode_layer_args(void) { return static_cast<int>(sizeof(me_decode_layer_args)); }

@@ -345,6 +345,7 @@ int launch_attn_bwd_simt(const me_attn_bwd_args* ba) {
         static_cast<const float*>(a->E), a->keypad, static_cast<const float*>(ba->dout), a->lse, ba->dsum,
         static_cast<float*>(ba->dk), static_cast<float*>(ba->dv), p);
   }
+  ++g_launch_count;
   ME_LAUNCH_CHECK();
   return 0;
 }

@@ -30,7 +30,12 @@ void set_error(const char* fmt, ...);
       return 1;                                                                        \
     }                                                                                  \
   } while (0)
-#define ME_LAUNCH_CHECK() ME_CUDA(cudaGetLastError())
+extern unsigned long long g_launch_count;  // kernels launched through this library (me_launch_count)
+#define ME_LAUNCH_CHECK()        \
+  do {                           \
+    ++me::g_launch_count;        \
+    ME_CUDA(cudaGetLastError()); \
+  } while (0)
 
 // ---------------------------------------------------------------------------------
 // small device utilities

@@ -105,8 +105,6 @@ using namespace me;
 extern "C" int me_layer_forward(const me_layer_args* a) {
   if (check_layer(a, "me_layer_forward")) return 1;
   ME_CHECK(a->Ls <= a->max_seq, "me_layer_forward: Ls %d > max_seq %d", a->Ls, a->max_seq);
-  ME_CHECK(!a->training || (a->z1 && a->z2 && a->mean1 && a->rstd1 && a->mean2 && a->rstd2 && a->lse),
-           "me_layer_forward: training needs z/mean/rstd/lse buffers");
   cudaStream_t st = static_cast<cudaStream_t>(a->stream);
   const int d = a->d, M = a->B * a->Ls, dt = a->dtype;
   if (linear(dt, a->x_T, a->Wqkv, a->qkv, M, 3 * d, d, d, d, 3 * d, 0, 0, false, ME_EPI_BIAS, a->bqkv, nullptr,

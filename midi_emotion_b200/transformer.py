@@ -1,0 +1,249 @@
+"""Emotion-conditioned MIDI-token transformer: the Python surface of the reference's model classes
+(models/music_multi.py:41-108 MusicTransformerMulti, models/music_continuous_token.py:32-105
+MusicTransformerContinuousToken) with the arithmetic done by the sm_100a kernels behind the C-ABI.
+
+* Same constructor keywords, attributes, `forward(x, condition)` signature and `state_dict` keys /
+  shapes as the reference, so checkpoints load unchanged.
+* No arithmetic happens in PyTorch: `forward` enqueues the C-ABI calls on the current CUDA stream;
+  `backward` is hand-derived (one `torch.autograd.Function` around the whole model) so that
+  `loss.backward()`, `clip_grad_norm_`, `optim.Adam` and DDP-style hooks see ordinary parameters.
+* Precision follows the caller the way the reference does: under `torch.autocast(..., bfloat16)`
+  (train.py:281, generate.py:116) the bf16 tensor-core path runs, otherwise the exact fp32 path.
+  `model.precision = "bf16" | "fp32"` overrides.
+* CUDA only.  A CPU tensor, a missing library or an unsupported shape raises; nothing falls back.
+"""
+from __future__ import annotations
+
+import math
+from typing import Dict, List, Optional
+
+import torch
+import torch.nn as nn
+
+from . import _lib
+from ._lib import ME_BF16, ME_F32, ptr
+
+MAX_SEQ = 2048
+LN_EPS = 1e-6
+
+_PE_CACHE: Dict[int, torch.Tensor] = {}
+
+
+def positional_table(d: int, max_seq: int = MAX_SEQ) -> torch.Tensor:
+    """[max_seq, d] fp32 sinusoid table, evaluated in float64 like models/music_multi.py:137-147
+    (angle = pos * e^{-ln(1e4) i/d} * e^{ln(1e4)/d (i%2)} + (pi/2)(i%2)) and cast to fp32 (:157-158).
+    It is not a parameter or buffer (absent from state_dict), exactly as in the reference."""
+    key = (d, max_seq)
+    if key not in _PE_CACHE:
+        ln = math.log(10000)
+        f = [math.exp(-ln * i / d) for i in range(d)]
+        g = [math.exp(ln / d * (i % 2)) for i in range(d)]
+        ph = [0.5 * math.pi * (i % 2) for i in range(d)]
+        sin = math.sin
+        rows = [[sin(pos * f[i] * g[i] + ph[i]) for i in range(d)] for pos in range(max_seq)]
+        _PE_CACHE[key] = torch.tensor(rows, dtype=torch.float64).to(torch.float32)
+    return _PE_CACHE[key]
+
+
+class _RelativeGlobalAttention(nn.Module):
+    """Parameter holder for models/music_multi.py:167-188 (Wq, Wk, Wv, fc, E)."""
+
+    def __init__(self, h: int, d: int, max_seq: int):
+        super().__init__()
+        self.h, self.d, self.dh, self.max_seq = h, d, d // h, max_seq
+        self.Wq = nn.Linear(d, d)
+        self.Wk = nn.Linear(d, d)
+        self.Wv = nn.Linear(d, d)
+        self.fc = nn.Linear(d, d)
+        self.E = nn.Parameter(torch.randn(max_seq, d // h))
+
+
+class _EncoderLayer(nn.Module):
+    """Parameter holder for models/music_multi.py:110-124."""
+
+    def __init__(self, d_model: int, d_inner: int, h: int, max_seq: int):
+        super().__init__()
+        self.rga = _RelativeGlobalAttention(h, d_model, max_seq)
+        self.FFN_pre = nn.Linear(d_model, d_inner)
+        self.FFN_suf = nn.Linear(d_inner, d_model)
+        self.layernorm1 = nn.LayerNorm(d_model, eps=LN_EPS)
+        self.layernorm2 = nn.LayerNorm(d_model, eps=LN_EPS)
+
+
+class MusicTransformer(nn.Module):
+    """One class for the four conditioning modes.
+
+    `continuous_token=True` reproduces MusicTransformerContinuousToken (two Linear(1, d) prefix
+    vectors, output length L+2); otherwise MusicTransformerMulti (d_condition > 0 = concat)."""
+
+    def __init__(self, embedding_dim=None, d_inner=None, d_condition=-1, vocab_size=None, num_layer=None,
+                 num_head=None, max_seq=MAX_SEQ, dropout=0.0, pad_token=0, continuous_token=False):
+        super().__init__()
+        assert embedding_dim % num_head == 0, "d_model must be divisible by n_head"
+        self.max_seq = max_seq
+        self.num_layer = num_layer
+        self.num_head = num_head
+        self.embedding_dim = embedding_dim
+        self.d_inner = d_inner
+        self.vocab_size = vocab_size
+        self.pad_token = pad_token
+        self.continuous_token = bool(continuous_token)
+        d_condition = 0 if (d_condition is None or d_condition < 0 or continuous_token) else d_condition
+        self.d_condition = d_condition
+        self.dropout_p = float(dropout)
+        self.precision = "auto"        # "auto" (follow torch autocast) | "fp32" | "bf16"
+        self.attn_impl = "auto"        # "auto" | "simt" | "tensor"
+
+        self.embedding = nn.Embedding(vocab_size, embedding_dim - d_condition, padding_idx=pad_token)
+        if self.continuous_token:
+            self.fc_condition = nn.ModuleList([nn.Linear(1, embedding_dim) for _ in range(2)])
+        elif d_condition > 0:
+            self.fc_condition = nn.Linear(2, d_condition)
+        self.enc_layers = nn.ModuleList(
+            [_EncoderLayer(embedding_dim, d_inner, num_head, max_seq) for _ in range(num_layer)])
+        self.fc = nn.Linear(embedding_dim, vocab_size)
+        self._init_weights()
+        self._wcache: Dict[int, dict] = {}
+        self._pe_dev: Optional[torch.Tensor] = None
+        self._step = 0
+
+    # ------------------------------------------------------------------ parameters
+    def _init_weights(self):
+        """models/music_multi.py:74-82, music_continuous_token.py:67-75: U(-0.1, 0.1) for the
+        embedding (including the pad row), head and condition weights; zero head/condition biases."""
+        r = 0.1
+        with torch.no_grad():
+            self.embedding.weight.uniform_(-r, r)
+            self.fc.bias.zero_()
+            self.fc.weight.uniform_(-r, r)
+            if self.continuous_token:
+                for lin in self.fc_condition:
+                    lin.weight.uniform_(-r, r)
+                    lin.bias.zero_()
+            elif self.d_condition > 0:
+                self.fc_condition.bias.zero_()
+                self.fc_condition.weight.uniform_(-r, r)
+
+    @property
+    def mode(self) -> int:
+        if self.continuous_token:
+            return _lib.COND_MODES["continuous_token"]
+        if self.d_condition > 0:
+            return _lib.COND_MODES["continuous_concat"]
+        return _lib.COND_MODES["none"]  # none / discrete_token are the same arithmetic
+
+    def _param_list(self) -> List[nn.Parameter]:
+        return [p for _, p in self.named_parameters()]
+
+    def _resolve_dtype(self) -> int:
+        if self.precision == "bf16":
+            return ME_BF16
+        if self.precision == "fp32":
+            return ME_F32
+        if torch.is_autocast_enabled("cuda"):
+            adt = torch.get_autocast_dtype("cuda")
+            if adt == torch.bfloat16:
+                return ME_BF16
+            raise RuntimeError("midi_emotion_b200: only bfloat16 autocast is supported (B200 path computes in bf16)")
+        return ME_F32
+
+    def _resolve_attn(self, dtype: int) -> int:
+        if self.attn_impl == "simt":
+            return _lib.ATTN_SIMT
+        if self.attn_impl == "tensor":
+            return _lib.ATTN_TENSOR
+        return _lib.ATTN_TENSOR if (dtype == ME_BF16 and _TENSOR_ATTENTION_AVAILABLE) else _lib.ATTN_SIMT
+
+    def invalidate_weight_cache(self):
+        self._wcache.clear()
+
+    def _weights(self, dtype: int) -> dict:
+        """Packed device copies of the parameters in the compute type (QKV concatenated, bf16 casts).
+        Rebuilt whenever a parameter's version counter moved (optimiser step, load_state_dict)."""
+        params = self._param_list()
+        versions = tuple(p._version for p in params) + tuple(p.data_ptr() for p in params)
+        wc = self._wcache.get(dtype)
+        if wc is not None and wc["versions"] == versions:
+            return wc
+        dev = params[0].device
+        tdt = torch.bfloat16 if dtype == ME_BF16 else torch.float32
+        stream = torch.cuda.current_stream().cuda_stream
+        d, di, V = self.embedding_dim, self.d_inner, self.vocab_size
+
+        def cast(dst, src):  # [rows, cols] fp32 parameter -> compute-type rows of dst
+            src = src.detach()
+            rows, cols = src.shape
+            _lib.call("me_convert_2d", ptr(src), ME_F32, cols, ptr(dst), dtype, dst.shape[1], rows, cols, stream)
+
+        if wc is None:
+            wc = {"layers": []}
+            for _ in range(self.num_layer):
+                wc["layers"].append({
+                    "Wqkv": torch.empty(3 * d, d, device=dev, dtype=tdt),
+                    "bqkv": torch.empty(3 * d, device=dev, dtype=torch.float32),
+                    "E": torch.empty(self.max_seq, d // self.num_head, device=dev, dtype=tdt),
+                    "Wo": torch.empty(d, d, device=dev, dtype=tdt),
+                    "W1": torch.empty(di, d, device=dev, dtype=tdt),
+                    "W2": torch.empty(d, di, device=dev, dtype=tdt),
+                })
+            wc["Wfc"] = torch.empty(V, d, device=dev, dtype=tdt)
+        with torch.no_grad():
+            for l, lay in enumerate(self.enc_layers):
+                w = wc["layers"][l]
+                for i, lin in enumerate((lay.rga.Wq, lay.rga.Wk, lay.rga.Wv)):
+                    cast(w["Wqkv"][i * d:(i + 1) * d], lin.weight)
+                    w["bqkv"][i * d:(i + 1) * d].copy_(lin.bias)
+                cast(w["E"], lay.rga.E)
+                cast(w["Wo"], lay.rga.fc.weight)
+                cast(w["W1"], lay.FFN_pre.weight)
+                cast(w["W2"], lay.FFN_suf.weight)
+            cast(wc["Wfc"], self.fc.weight)
+        wc["versions"] = versions
+        self._wcache[dtype] = wc
+        return wc
+
+    def _pe(self, device) -> torch.Tensor:
+        if self._pe_dev is None or self._pe_dev.device != device:
+            self._pe_dev = positional_table(self.embedding_dim, self.max_seq).to(device)
+        return self._pe_dev
+
+    def _cond_params(self):
+        """(cw0, cb0, cw1, cb1) pointers' tensors for the input stage."""
+        if self.continuous_token:
+            a, b = self.fc_condition[0], self.fc_condition[1]
+            return a.weight, a.bias, b.weight, b.bias
+        if self.d_condition > 0:
+            return self.fc_condition.weight, self.fc_condition.bias, None, None
+        return None, None, None, None
+
+    # ------------------------------------------------------------------ forward
+    def forward(self, x: torch.Tensor, condition: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """x: int64 [B, L] token ids (pad = 0); condition: float [B, 2] (valence, arousal), ignored
+        (may be NaN) for none/discrete_token.  Returns logits [B, Ls, V] (Ls = L+2 for
+        continuous_token): fp32 on the fp32 path, bf16 under bf16 autocast (as the reference)."""
+        if not x.is_cuda:
+            raise RuntimeError("midi_emotion_b200: CUDA tensors required (there is no CPU fallback)")
+        if x.dtype != torch.int64 or x.dim() != 2:
+            raise RuntimeError("midi_emotion_b200: x must be int64 [batch, sequence]")
+        if self.mode != 0:
+            if condition is None or condition.shape != (x.shape[0], 2):
+                raise RuntimeError("midi_emotion_b200: condition must be float [batch, 2]")
+            condition = condition.to(device=x.device, dtype=torch.float32).contiguous()
+        else:
+            condition = None
+        from .autograd import model_apply
+        return model_apply(self, x.contiguous(), condition)
+
+    def extra_repr(self) -> str:
+        return (f"d_model={self.embedding_dim}, d_inner={self.d_inner}, d_condition={self.d_condition}, "
+                f"layers={self.num_layer}, heads={self.num_head}, vocab={self.vocab_size}, "
+                f"continuous_token={self.continuous_token}, dropout={self.dropout_p}")
+
+
+_TENSOR_ATTENTION_AVAILABLE = False
+
+
+def set_dropout(model: MusicTransformer, rate: float) -> MusicTransformer:
+    """models/build_model.py:2-7 equivalent: the model keeps a single dropout rate."""
+    model.dropout_p = float(rate)
+    return model

@@ -1,0 +1,294 @@
+"""Kernel-level parity on the B200 (through the C-ABI): tcgen05 GEMM, fp32 GEMM, LayerNorm, input
+stage and relative attention, each against a straightforward fp32 evaluation of the same maths."""
+import ctypes as C
+import math
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+if torch.cuda.is_available():
+    from gpu_util import dev, gemm_bf16, rel_err, stream
+    from midi_emotion_b200 import _lib
+    from midi_emotion_b200._lib import ME_BF16, ME_F32, ptr
+    from oracle import midi_oracle as O
+
+
+def _operands(M, N, K, a_mn, b_mn, seed=0):
+    g = torch.Generator(device="cuda").manual_seed(seed)
+    A = torch.randn(M, K, device="cuda", generator=g).to(torch.bfloat16)
+    B = torch.randn(N, K, device="cuda", generator=g).to(torch.bfloat16)
+    As = A.t().contiguous() if a_mn else A
+    Bs = B.t().contiguous() if b_mn else B
+    return A, B, As, Bs
+
+
+GEMM_SHAPES = [
+    # M, N, K, a_mn, b_mn, tile_n
+    (128, 256, 64, 0, 0, 256),
+    (128, 128, 128, 0, 0, 128),
+    (256, 64, 192, 0, 0, 64),
+    (384, 32, 64, 0, 0, 32),
+    (200, 1007, 96, 0, 0, 0),        # ragged M, N, K (head GEMM, V = 1007, d = 96)
+    (520, 2304, 768, 0, 0, 0),       # QKV projection shape
+    (300, 3072, 768, 0, 0, 256),
+    (256, 768, 3072, 0, 0, 128),
+    (256, 256, 128, 0, 1, 256),      # dgrad: B stored [K, N]
+    (333, 768, 3072, 0, 1, 128),
+    (130, 64, 128, 0, 1, 128),       # N smaller than the tile
+    (768, 3072, 512, 1, 1, 256),     # wgrad: both stored [K, rows]
+    (1007, 96, 300, 1, 1, 128),      # head wgrad, ragged everything
+    (96, 192, 74, 1, 1, 128),
+]
+
+
+@pytest.mark.parametrize("M,N,K,a_mn,b_mn,tile_n", GEMM_SHAPES)
+def test_gemm_tcgen05_matches_fp32(M, N, K, a_mn, b_mn, tile_n):
+    A, B, As, Bs = _operands(M, N, K, a_mn, b_mn)
+    want = A.float() @ B.float().t()
+    got = gemm_bf16(As, Bs, M, N, K, a_mn, b_mn, ME_F32, tile_n=tile_n)
+    torch.cuda.synchronize()
+    assert torch.isfinite(got).all()
+    assert rel_err(got, want) < 1e-5, rel_err(got, want)
+    assert (got - want).abs().max() <= 1e-3 * max(1.0, math.sqrt(K))
+
+
+def test_gemm_tcgen05_against_device_reference_kernel():
+    M, N, K = 257, 515, 200
+    A, B, As, Bs = _operands(M, N, K, 0, 0, seed=3)
+    ref = torch.empty(M, N, device="cuda")
+    _lib.call("me_gemm_bf16_reference", ptr(As), ptr(Bs), ptr(ref), M, N, K, K, K, N, 0, 0, stream())
+    got = gemm_bf16(As, Bs, M, N, K, 0, 0, ME_F32)
+    torch.cuda.synchronize()
+    assert rel_err(got, ref) < 2e-6
+
+
+@pytest.mark.parametrize("flags", ["bias", "bias_relu", "bias_add", "mask"])
+@pytest.mark.parametrize("out_dtype", ["f32", "bf16"])
+def test_gemm_epilogues(flags, out_dtype):
+    M, N, K = 300, 520, 256
+    A, B, As, Bs = _operands(M, N, K, 0, 0, seed=5)
+    bias = torch.randn(N, device="cuda")
+    addend = torch.randn(M, N, device="cuda")
+    mask = torch.randn(M, N, device="cuda").to(torch.bfloat16)
+    od = ME_F32 if out_dtype == "f32" else ME_BF16
+    want = A.float() @ B.float().t()
+    f = 0
+    kw = {}
+    if "bias" in flags:
+        f |= _lib.EPI_BIAS
+        want = want + bias
+        kw["bias"] = bias
+    if "add" in flags:
+        f |= _lib.EPI_ADD_F32
+        want = want + addend
+        kw["addend"] = addend
+    if "relu" in flags:
+        f |= _lib.EPI_RELU
+        want = want.relu()
+    if flags == "mask":
+        f |= _lib.EPI_RELU_MASK
+        want = torch.where(mask.float() > 0, want, torch.zeros_like(want))
+        kw["mask"] = mask
+    got = gemm_bf16(As, Bs, M, N, K, 0, 0, od, flags=f, **kw)
+    torch.cuda.synchronize()
+    if od == ME_BF16:
+        assert torch.equal(got, want.to(torch.bfloat16)) or rel_err(got.float(), want) < 3e-3
+    else:
+        assert rel_err(got, want) < 1e-5
+
+
+def test_gemm_split_k_matches_single_pass():
+    M, N, K = 256, 512, 4096
+    A, B, As, Bs = _operands(M, N, K, 1, 1, seed=7)
+    one = gemm_bf16(As, Bs, M, N, K, 1, 1, ME_F32, tile_n=256, splits=1)
+    four = gemm_bf16(As, Bs, M, N, K, 1, 1, ME_F32, tile_n=256, splits=4)
+    torch.cuda.synchronize()
+    assert rel_err(four, one) < 1e-6
+    assert rel_err(one, A.float() @ B.float().t()) < 1e-5
+
+
+def test_gemm_rejects_misaligned_operands():
+    A = torch.zeros(64, 70, device="cuda", dtype=torch.bfloat16)  # pitch 70 elements: not 16-byte aligned
+    B = torch.zeros(64, 70, device="cuda", dtype=torch.bfloat16)
+    with pytest.raises(RuntimeError, match="multiples of 8"):
+        gemm_bf16(A, B, 64, 64, 70, 0, 0, ME_F32)
+
+
+@pytest.mark.parametrize("a_mn,b_mn", [(0, 0), (0, 1), (1, 1), (1, 0)])
+def test_gemm_f32_simt(a_mn, b_mn):
+    M, N, K = 150, 203, 77
+    g = torch.Generator(device="cuda").manual_seed(1)
+    A = torch.randn(M, K, device="cuda", generator=g)
+    B = torch.randn(N, K, device="cuda", generator=g)
+    As = A.t().contiguous() if a_mn else A
+    Bs = B.t().contiguous() if b_mn else B
+    bias = torch.randn(N, device="cuda")
+    D = torch.empty(M, N, device="cuda")
+    _lib.call("me_gemm_f32", ptr(As), ptr(Bs), ptr(D), M, N, K, As.stride(0), Bs.stride(0), N, a_mn, b_mn,
+              _lib.EPI_BIAS | _lib.EPI_RELU, ptr(bias), None, None, 0, stream())
+    want = (A.double() @ B.double().t() + bias.double()).relu()
+    assert rel_err(D, want) < 1e-6
+
+
+@pytest.mark.parametrize("dtype", ["f32", "bf16"])
+@pytest.mark.parametrize("d", [64, 96, 768, 1024])
+def test_add_layernorm_forward_backward(dtype, d):
+    M = 77
+    dt = ME_F32 if dtype == "f32" else ME_BF16
+    tdt = torch.float32 if dtype == "f32" else torch.bfloat16
+    g = torch.Generator(device="cuda").manual_seed(d)
+    x = torch.randn(M, d, device="cuda", generator=g)
+    y = torch.randn(M, d, device="cuda", generator=g).to(tdt)
+    gamma = torch.randn(d, device="cuda", generator=g)
+    beta = torch.randn(d, device="cuda", generator=g)
+    out = torch.empty(M, d, device="cuda")
+    out_T = out if dtype == "f32" else torch.empty(M, d, device="cuda", dtype=tdt)
+    z = torch.empty(M, d, device="cuda")
+    mean = torch.empty(M, device="cuda")
+    rstd = torch.empty(M, device="cuda")
+    _lib.call("me_add_layernorm_forward", ptr(x), ptr(y), dt, ptr(gamma), ptr(beta), 1e-6, M, d, 0.0, 0, ptr(out),
+              ptr(out_T), ptr(z), ptr(mean), ptr(rstd), stream())
+    xr = x.double().requires_grad_(True)
+    yr = y.double().requires_grad_(True)
+    gr = gamma.double().requires_grad_(True)
+    br = beta.double().requires_grad_(True)
+    want = torch.nn.functional.layer_norm(xr + yr, (d,), gr, br, 1e-6)
+    assert rel_err(out, want.detach()) < 2e-6
+    if dtype == "bf16":
+        assert torch.equal(out_T, out.to(torch.bfloat16))
+    dout = torch.randn(M, d, device="cuda", generator=g)
+    want.backward(dout.double())
+    dz = torch.empty(M, d, device="cuda")
+    dy_T = torch.empty(M, d, device="cuda", dtype=tdt)
+    dgam = torch.zeros(d, device="cuda")
+    dbet = torch.zeros(d, device="cuda")
+    _lib.call("me_add_layernorm_backward", ptr(dout), None, ptr(z), ptr(mean), ptr(rstd), ptr(gamma), M, d, 0.0, 0, dt,
+              ptr(dz), ptr(dy_T), ptr(dgam), ptr(dbet), stream())
+    assert rel_err(dz, xr.grad) < 1e-5
+    assert rel_err(dy_T.float(), yr.grad) < (1e-5 if dtype == "f32" else 5e-3)
+    assert rel_err(dgam, gr.grad) < 1e-5
+    assert rel_err(dbet, br.grad) < 1e-5
+
+
+def test_add_layernorm_dropout_is_consistent_between_forward_and_backward():
+    M, d, p = 64, 256, 0.25
+    x = torch.zeros(M, d, device="cuda")
+    y = torch.ones(M, d, device="cuda")
+    gamma = torch.ones(d, device="cuda")
+    beta = torch.zeros(d, device="cuda")
+    out = torch.empty(M, d, device="cuda")
+    z = torch.empty(M, d, device="cuda")
+    mean = torch.empty(M, device="cuda")
+    rstd = torch.empty(M, device="cuda")
+    _lib.call("me_add_layernorm_forward", ptr(x), ptr(y), ME_F32, ptr(gamma), ptr(beta), 1e-6, M, d, p, 1234, ptr(out),
+              ptr(out), ptr(z), ptr(mean), ptr(rstd), stream())
+    keep = z != 0
+    frac = keep.float().mean().item()
+    assert abs(frac - (1 - p)) < 0.02
+    assert torch.allclose(z[keep], torch.full_like(z[keep], 1 / (1 - p)))
+    # backward: dy = mask/(1-p) * dz, same mask
+    dout = torch.randn(M, d, device="cuda")
+    dz = torch.empty(M, d, device="cuda")
+    dy = torch.empty(M, d, device="cuda")
+    dg = torch.zeros(d, device="cuda")
+    db = torch.zeros(d, device="cuda")
+    _lib.call("me_add_layernorm_backward", ptr(dout), None, ptr(z), ptr(mean), ptr(rstd), ptr(gamma), M, d, p, 1234,
+              ME_F32, ptr(dz), ptr(dy), ptr(dg), ptr(db), stream())
+    assert torch.equal(dy != 0, keep & (dz != 0))
+    assert torch.allclose(dy[keep], dz[keep] / (1 - p))
+
+
+def _attn_reference(q, k, v, E, keypad, max_seq):
+    """fp64 evaluation of S = (QK^T + Srel)/sqrt(dh), causal + key-pad mask, softmax, PV."""
+    B, H, L, dh = q.shape
+    q, k, v, E = q.double(), k.double(), v.double(), E.double()
+    i = torch.arange(L, device=q.device)[:, None]
+    j = torch.arange(L, device=q.device)[None, :]
+    idx = (max_seq - 1 - (i - j)).clamp(0, max_seq - 1)
+    Eg = E[idx]                                            # [L, L, dh]
+    srel = torch.einsum("bhid,ijd->bhij", q, Eg)
+    s = (q @ k.transpose(-1, -2) + srel) / math.sqrt(dh)
+    mask = (j > i)[None, None] | keypad.bool()[:, None, None, :]
+    s = s.masked_fill(mask, float("-inf"))
+    return torch.softmax(s, -1) @ v
+
+
+@pytest.mark.parametrize("dtype", ["f32", "bf16"])
+@pytest.mark.parametrize("B,H,L,dh", [(2, 2, 37, 48), (1, 3, 130, 64), (2, 1, 64, 32)])
+def test_attention_simt_forward_backward(dtype, B, H, L, dh):
+    dt = ME_F32 if dtype == "f32" else ME_BF16
+    tdt = torch.float32 if dtype == "f32" else torch.bfloat16
+    MS = 2048
+    d = H * dh
+    g = torch.Generator(device="cuda").manual_seed(L)
+    qkv = (torch.randn(B, L, 3, H, dh, device="cuda", generator=g) * 0.7).to(tdt)
+    E = (torch.randn(MS, dh, device="cuda", generator=g) * 0.3).to(tdt)
+    keypad = torch.zeros(B, L, device="cuda", dtype=torch.uint8)
+    keypad[0, L - 5:] = 1
+    out = torch.empty(B, L, d, device="cuda", dtype=tdt)
+    lse = torch.empty(B, H, L, device="cuda")
+    a = _lib.AttnArgs()
+    a.dtype, a.impl = dt, _lib.ATTN_SIMT
+    a.B, a.H, a.Lq, a.Lk, a.dh, a.max_seq, a.q_pos0 = B, H, L, L, dh, MS, 0
+    es = qkv.element_size()
+    a.q, a.k, a.v, a.E = qkv.data_ptr(), qkv.data_ptr() + d * es, qkv.data_ptr() + 2 * d * es, E.data_ptr()
+    for n in "qkv":
+        setattr(a, f"{n}_sb", L * 3 * d)
+        setattr(a, f"{n}_sh", dh)
+    a.q_si = a.k_sj = a.v_sj = 3 * d
+    a.keypad, a.keypad_ld = keypad.data_ptr(), L
+    a.out, a.o_sb, a.o_si = out.data_ptr(), L * d, d
+    a.lse, a.pos_dev, a.stream = lse.data_ptr(), None, stream()
+    _lib.call("me_attention_forward", C.byref(a))
+
+    q = qkv[:, :, 0].permute(0, 2, 1, 3).float().requires_grad_(True)
+    k = qkv[:, :, 1].permute(0, 2, 1, 3).float().requires_grad_(True)
+    v = qkv[:, :, 2].permute(0, 2, 1, 3).float().requires_grad_(True)
+    Er = E.float().requires_grad_(True)
+    want = _attn_reference(q, k, v, Er, keypad, MS)         # [B,H,L,dh]
+    want_m = want.permute(0, 2, 1, 3).reshape(B, L, d)
+    tol = 1e-5 if dtype == "f32" else 6e-3
+    assert rel_err(out.float(), want_m.detach()) < tol
+
+    dout = (torch.randn(B, L, d, device="cuda", generator=g)).to(tdt)
+    want_m.backward(dout.double())
+    g_qkv = torch.zeros_like(qkv)
+    dE = torch.zeros(MS, dh, device="cuda")
+    dsum = torch.empty(B, H, L, device="cuda")
+    ba = _lib.AttnBwdArgs()
+    ba.f = a
+    ba.dout = dout.data_ptr()
+    ba.dq, ba.dk, ba.dv = g_qkv.data_ptr(), g_qkv.data_ptr() + d * es, g_qkv.data_ptr() + 2 * d * es
+    ba.dE, ba.dsum = dE.data_ptr(), dsum.data_ptr()
+    _lib.call("me_attention_backward", C.byref(ba))
+    tol = 2e-5 if dtype == "f32" else 1e-2
+    assert rel_err(g_qkv[:, :, 0].permute(0, 2, 1, 3).float(), q.grad) < tol
+    assert rel_err(g_qkv[:, :, 1].permute(0, 2, 1, 3).float(), k.grad) < tol
+    assert rel_err(g_qkv[:, :, 2].permute(0, 2, 1, 3).float(), v.grad) < tol
+    assert rel_err(dE, Er.grad) < tol
+
+
+def test_embed_forward_matches_oracle(golden):
+    g = golden
+    cfg = g["cfg"]
+    from midi_emotion_b200 import build_model
+    model, _ = build_model(dict(cfg))
+    model.load_state_dict(g["params"])
+    model = model.cuda().eval()
+    want, mask = O.embed(g["params"], cfg, g["tokens"], g["cond"])
+    tokens = g["tokens"].cuda()
+    B, L = tokens.shape
+    Ls, d = want.shape[1], want.shape[2]
+    x = torch.empty(B * Ls, d, device="cuda")
+    keypad = torch.empty(B, Ls, device="cuda", dtype=torch.uint8)
+    cw0, cb0, cw1, cb1 = model._cond_params()
+    cond = g["cond"].cuda() if model.mode != 0 else None
+    _lib.call("me_embed_forward", ptr(tokens), ptr(cond), ptr(model.embedding.weight), ptr(cw0), ptr(cb0), ptr(cw1),
+              ptr(cb1), ptr(model._pe(tokens.device)), B, L, d, model.d_condition, cfg["vocab_size"], model.mode, 0,
+              0.0, 0, ME_F32, ptr(x), ptr(x), ptr(keypad), stream())
+    got = x.view(B, Ls, d).cpu()
+    assert torch.allclose(got, want, rtol=0, atol=1e-6), (got - want).abs().max()
+    # key-pad bitmap == last query row of the reference mask (row Ls-1 has no causal masking)
+    assert torch.equal(keypad.cpu().bool(), mask[:, -1, :])
