@@ -47,6 +47,10 @@ int me_version(void);
 unsigned long long me_launch_count(void);
 /* 1 when the running device is sm_100 (B200); the tcgen05 paths refuse to run otherwise. */
 int me_device_is_sm100(void);
+/* Live timing of the tcgen05 GEMM launches (bench.py's roofline figure): enable with a slot count,
+ * run, then collect the summed CUDA-event durations, algorithmic FLOPs (2MNK) and launch count. */
+int me_profile_enable(int capacity);
+int me_profile_collect(double* total_ms, double* total_flops, int* launches);
 /* sizeof() of the argument structs below, for binding self-checks (ctypes/cgo/JNI mirrors). */
 int me_sizeof_attn_args(void);
 int me_sizeof_attn_bwd_args(void);

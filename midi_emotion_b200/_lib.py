@@ -69,6 +69,8 @@ _PROTOS = {
     "me_version": (C.c_int, []),
     "me_launch_count": (C.c_ulonglong, []),
     "me_device_is_sm100": (C.c_int, []),
+    "me_profile_enable": (C.c_int, [C.c_int]),
+    "me_profile_collect": (C.c_int, [C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_int)]),
     "me_sizeof_attn_args": (C.c_int, []),
     "me_sizeof_attn_bwd_args": (C.c_int, []),
     "me_sizeof_layer_args": (C.c_int, []),

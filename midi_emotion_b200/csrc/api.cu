@@ -119,3 +119,61 @@ extern "C" int me_sizeof_attn_bwd_args(void) { return static_cast<int>(sizeof(me
 extern "C" int me_sizeof_layer_args(void) { return static_cast<int>(sizeof(me_layer_args)); }
 extern "C" int me_sizeof_layer_bwd_args(void) { return static_cast<int>(sizeof(me_layer_bwd_args)); }
 extern "C" int me_sizeof_decode_layer_args(void) { return static_cast<int>(sizeof(me_decode_layer_args)); }
+
+// ---------------------------------------------------------------------------------------------
+// Live kernel timing for bench.py: while enabled, every tcgen05 GEMM launch is bracketed by CUDA
+// events on its own stream; me_profile_collect() sums durations and algorithmic FLOPs.
+// ---------------------------------------------------------------------------------------------
+namespace me {
+struct ProfSlot { cudaEvent_t a, b; double flops; };
+static ProfSlot* g_prof = nullptr;
+static int g_prof_cap = 0, g_prof_n = 0, g_prof_on = 0;
+
+cudaEvent_t prof_begin(double flops, cudaStream_t st) {
+  if (!g_prof_on || g_prof_n >= g_prof_cap) return nullptr;
+  ProfSlot& s = g_prof[g_prof_n];
+  s.flops = flops;
+  cudaEventRecord(s.a, st);
+  return s.b;
+}
+void prof_end(cudaEvent_t e, cudaStream_t st) {
+  if (!e) return;
+  cudaEventRecord(e, st);
+  ++g_prof_n;
+}
+}  // namespace me
+
+extern "C" int me_profile_enable(int capacity) {
+  using namespace me;
+  if (capacity > g_prof_cap) {
+    ProfSlot* n = static_cast<ProfSlot*>(realloc(g_prof, sizeof(ProfSlot) * capacity));
+    ME_CHECK(n != nullptr, "me_profile_enable: out of memory");
+    g_prof = n;
+    for (int i = g_prof_cap; i < capacity; ++i) {
+      ME_CUDA(cudaEventCreate(&g_prof[i].a));
+      ME_CUDA(cudaEventCreate(&g_prof[i].b));
+    }
+    g_prof_cap = capacity;
+  }
+  g_prof_n = 0;
+  g_prof_on = capacity > 0 ? 1 : 0;
+  return 0;
+}
+
+extern "C" int me_profile_collect(double* total_ms, double* total_flops, int* launches) {
+  using namespace me;
+  double ms = 0, fl = 0;
+  for (int i = 0; i < g_prof_n; ++i) {
+    ME_CUDA(cudaEventSynchronize(g_prof[i].b));
+    float t = 0.f;
+    ME_CUDA(cudaEventElapsedTime(&t, g_prof[i].a, g_prof[i].b));
+    ms += t;
+    fl += g_prof[i].flops;
+  }
+  if (total_ms) *total_ms = ms;
+  if (total_flops) *total_flops = fl;
+  if (launches) *launches = g_prof_n;
+  g_prof_n = 0;
+  g_prof_on = 0;
+  return 0;
+}

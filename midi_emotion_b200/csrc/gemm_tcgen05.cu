@@ -17,6 +17,9 @@
 
 namespace me {
 
+cudaEvent_t prof_begin(double flops, cudaStream_t st);
+void prof_end(cudaEvent_t e, cudaStream_t st);
+
 constexpr int G_BM = 128;
 constexpr int G_BK = 64;
 constexpr int G_THREADS = 192;  // warp0: TMA, warp1: MMA + TMEM alloc, warps 2..5: epilogue
@@ -345,8 +348,13 @@ int launch_gemm_bf16(const void* A, const void* B, void* D, int M, int N, int K,
   const int total = num_m_tiles * num_n_tiles * splits;
   const int grid = total < sms ? total : sms;
 
-#define ME_GEMM_CASE(BNV, AMN, BMN) \
-  if (bn == BNV && a_mn == AMN && b_mn == BMN) return launch_one<BNV, (AMN != 0), (BMN != 0)>(tmA, tmB, p, grid, st);
+  cudaEvent_t pe = prof_begin(2.0 * M * N * K, st);
+#define ME_GEMM_CASE(BNV, AMN, BMN)                                                   \
+  if (bn == BNV && a_mn == AMN && b_mn == BMN) {                                      \
+    const int rc = launch_one<BNV, (AMN != 0), (BMN != 0)>(tmA, tmB, p, grid, st);    \
+    prof_end(pe, st);                                                                 \
+    return rc;                                                                        \
+  }
   ME_GEMM_CASE(256, 0, 0)
   ME_GEMM_CASE(128, 0, 0)
   ME_GEMM_CASE(64, 0, 0)

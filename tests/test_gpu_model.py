@@ -48,10 +48,13 @@ def test_backward_fp32_matches_reference_golden(golden):
                                              ignore_index=0)
     loss.backward()
     assert abs(loss.item() - g["loss_fp32"]) < 2e-5
+    # rga.Wk.bias has an identically-zero gradient (softmax is invariant to a per-row constant), so
+    # the reference holds only rounding noise there: scale errors by the largest gradient as well
+    floor = 1e-4 * max(v.abs().max().item() for v in g["grads"].values())
     for name, p in model.named_parameters():
         ref = g["grads"][name]
         got = p.grad.cpu()
-        denom = max(ref.abs().max().item(), 1e-8)
+        denom = max(ref.abs().max().item(), floor)
         assert (got - ref).abs().max().item() / denom < 5e-4, name
 
 
@@ -132,6 +135,8 @@ def test_train_step_matches_oracle_train_step(golden):
         # Adam's first step moves every weight by ~lr*sign(g): compare the update, not the weight
         upd_got = p.detach().cpu() - g["params"][name]
         upd_want = want[name] - g["params"][name]
+        if name.endswith("rga.Wk.bias"):
+            continue  # zero gradient up to rounding noise: Adam turns the noise's sign into a step
         big = g["grads"][name].abs() > 1e-4 * g["grads"][name].abs().max().clamp_min(1e-12)
         if big.any():
             assert torch.allclose(upd_got[big], upd_want[big], rtol=2e-2, atol=2e-5), name
