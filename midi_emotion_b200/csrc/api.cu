@@ -77,6 +77,27 @@ int make_tmap_3d_bf16(CUtensorMap* out, const void* base, uint64_t d0, uint64_t 
   return 0;
 }
 
+int make_tmap_nd_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims,
+                      const uint64_t* strides_elems, const uint32_t* box) {
+  EncodeTiledFn fn = encode_fn();
+  ME_CHECK(fn != nullptr, "cuTensorMapEncodeTiled entry point not available");
+  ME_CHECK(rank >= 1 && rank <= 5, "tensor map rank %d", rank);
+  ME_CHECK((reinterpret_cast<uintptr_t>(base) & 15) == 0, "tensor map base must be 16-byte aligned");
+  cuuint64_t d[5], st[4];
+  cuuint32_t bx[5], es[5];
+  for (int i = 0; i < rank; ++i) { d[i] = dims[i]; bx[i] = box[i]; es[i] = 1; }
+  for (int i = 0; i + 1 < rank; ++i) {
+    ME_CHECK(strides_elems[i] % 8 == 0, "tensor map stride %d (%llu elements) must be a multiple of 8", i,
+             (unsigned long long)strides_elems[i]);
+    st[i] = strides_elems[i] * 2;
+  }
+  CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, rank, const_cast<void*>(base), d, st, bx, es,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  ME_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(rank %d) failed: %d", rank, static_cast<int>(r));
+  return 0;
+}
+
 int launch_attn_fwd_simt(const me_attn_args* a);
 int launch_attn_bwd_simt(const me_attn_bwd_args* a);
 int launch_attn_fwd_tc(const me_attn_args* a);

@@ -3,7 +3,8 @@
 mkdir -p gpurun_out
 nvidia-smi --query-gpu=name,memory.total,clocks.max.sm --format=csv > gpurun_out/gpu.txt 2>&1
 run() { name=$1; shift; echo "=== $name"; timeout 600 python -m pytest "$@" -q -m gpu --timeout 180 -p no:cacheprovider > gpurun_out/$name.log 2>&1; echo "exit $?"; tail -n 25 gpurun_out/$name.log; }
-run simt tests/test_gpu_kernels.py -k "not tcgen05 and not epilogues and not split_k and not rejects"
+run simt tests/test_gpu_kernels.py -k "not tcgen05 and not epilogues and not split_k and not rejects and not tensor_core"
 run tcgen05 tests/test_gpu_kernels.py -k "tcgen05 or epilogues or split_k or rejects"
+run attn_tc tests/test_gpu_kernels.py -k "tensor_core"
 run model_fp32 tests/test_gpu_model.py -k "not bf16"
 run model_bf16 tests/test_gpu_model.py -k "bf16"

@@ -299,3 +299,54 @@ def test_embed_forward_matches_oracle(golden):
     assert torch.allclose(got, want, rtol=0, atol=1e-6), (got - want).abs().max()
     # key-pad bitmap == last query row of the reference mask (row Ls-1 has no causal masking)
     assert torch.equal(keypad.cpu().bool(), mask[:, -1, :])
+
+
+def _run_attention_forward(impl, qkv, E, keypad, B, H, L, dh):
+    MS = E.shape[0]
+    d = H * dh
+    out = torch.full((B, L, d), float("nan"), device="cuda", dtype=qkv.dtype)
+    lse = torch.empty(B, H, L, device="cuda")
+    a = _lib.AttnArgs()
+    a.dtype, a.impl = (ME_F32 if qkv.dtype == torch.float32 else ME_BF16), impl
+    a.B, a.H, a.Lq, a.Lk, a.dh, a.max_seq, a.q_pos0 = B, H, L, L, dh, MS, 0
+    es = qkv.element_size()
+    a.q, a.k, a.v, a.E = qkv.data_ptr(), qkv.data_ptr() + d * es, qkv.data_ptr() + 2 * d * es, E.data_ptr()
+    for n in "qkv":
+        setattr(a, f"{n}_sb", L * 3 * d)
+        setattr(a, f"{n}_sh", dh)
+    a.q_si = a.k_sj = a.v_sj = 3 * d
+    a.keypad, a.keypad_ld = (keypad.data_ptr() if keypad is not None else None), L
+    a.out, a.o_sb, a.o_si = out.data_ptr(), L * d, d
+    a.lse, a.pos_dev, a.stream = lse.data_ptr(), None, stream()
+    _lib.call("me_attention_forward", C.byref(a))
+    return out, lse, a
+
+
+TC_ATTN_SHAPES = [(2, 2, 37, 48), (1, 3, 130, 64), (2, 1, 64, 32), (2, 2, 300, 64), (1, 2, 1024, 64),
+                  (1, 1, 2048, 64), (3, 2, 129, 32), (2, 4, 1026, 48)]
+
+
+@pytest.mark.parametrize("B,H,L,dh", TC_ATTN_SHAPES)
+@pytest.mark.parametrize("pad", [False, True])
+def test_attention_tensor_core_forward(B, H, L, dh, pad):
+    MS = 2048
+    g = torch.Generator(device="cuda").manual_seed(L * 7 + dh)
+    qkv = (torch.randn(B, L, 3, H, dh, device="cuda", generator=g) * 0.8).to(torch.bfloat16)
+    E = (torch.randn(MS, dh, device="cuda", generator=g) * 0.3).to(torch.bfloat16)
+    keypad = torch.zeros(B, L, device="cuda", dtype=torch.uint8)
+    if pad:
+        keypad[0, L - min(L // 3, 70):] = 1
+        keypad[B - 1, 1::5] = 1
+    out, lse, _ = _run_attention_forward(_lib.ATTN_TENSOR, qkv, E, keypad if pad else None, B, H, L, dh)
+    q = qkv[:, :, 0].permute(0, 2, 1, 3).float()
+    k = qkv[:, :, 1].permute(0, 2, 1, 3).float()
+    v = qkv[:, :, 2].permute(0, 2, 1, 3).float()
+    want = _attn_reference(q, k, v, E.float(), keypad, MS).permute(0, 2, 1, 3).reshape(B, L, H * dh)
+    torch.cuda.synchronize()
+    assert torch.isfinite(out.float()).all()
+    assert rel_err(out.float(), want) < 8e-3, rel_err(out.float(), want)
+    assert (out.float() - want).abs().max() < 0.05
+    # the two implementations agree on the log-sum-exp they hand to backward
+    out2, lse2, _ = _run_attention_forward(_lib.ATTN_SIMT, qkv, E, keypad if pad else None, B, H, L, dh)
+    assert torch.allclose(lse, lse2, rtol=1e-3, atol=2e-3), (lse - lse2).abs().max()
+    assert rel_err(out.float(), out2.float()) < 8e-3
