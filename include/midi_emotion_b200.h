@@ -158,13 +158,15 @@ int me_attention_forward(const me_attn_args* a);
 
 /* Backward of the above (full self-attention only, q_pos0 = 0, Lq = Lk).
  *   dout T same addressing as out; dq/dk/dv T with the q/k/v strides; dE f32 [max_seq, dh]
- *   accumulates (+=, caller zeroes); dsum f32 [B,H,Lq] is scratch. */
+ *   accumulates (+=, caller zeroes); dsum f32 [B,H,Lq] is scratch; dq_acc f32 [B, Lq, H*dh] is
+ *   scratch needed by ME_ATTN_TENSOR only (fp32 accumulation of dq across key tiles). */
 typedef struct me_attn_bwd_args {
   me_attn_args f;
   const void* dout;
   void *dq, *dk, *dv;
   float* dE;
   float* dsum;
+  float* dq_acc;
 } me_attn_bwd_args;
 int me_attention_backward(const me_attn_bwd_args* a);
 

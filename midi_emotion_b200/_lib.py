@@ -35,7 +35,7 @@ class AttnArgs(C.Structure):
 
 
 class AttnBwdArgs(C.Structure):
-    _fields_ = [("f", AttnArgs), ("dout", _vp), ("dq", _vp), ("dk", _vp), ("dv", _vp), ("dE", _vp), ("dsum", _vp)]
+    _fields_ = [("f", AttnArgs), ("dout", _vp), ("dq", _vp), ("dk", _vp), ("dv", _vp), ("dE", _vp), ("dsum", _vp), ("dq_acc", _vp)]
 
 
 _LAYER_PTRS = ["x_f32", "x_T", "keypad", "Wqkv", "bqkv", "E", "Wo", "bo", "ln1_w", "ln1_b", "W1", "b1", "W2", "b2",

@@ -17,8 +17,7 @@
 //   * online softmax in fp32 (exp2, running max/sum per row = per thread, no shuffles needed);
 //   * P (bf16) goes to shared memory in the UMMA K-major layout, O_tile = P V (N = dh) lands in TMEM
 //     and is folded into the fp32 output accumulator held in registers.
-#include "common.cuh"
-#include "../../include/midi_emotion_b200.h"
+#include "attention_tc.cuh"
 
 namespace me {
 
@@ -43,28 +42,6 @@ struct FaParams {
   float* lse;
   float scale_log2;  // log2(e) / sqrt(dh)
 };
-
-// out[b] = r[b + s] for b < 32, s in [0, 31]: five conditional shifts by 16, 8, 4, 2, 1.
-// (selp through inline PTX: left to itself the compiler turns the first stage into a dynamically
-// indexed local-memory array.)
-__device__ __forceinline__ uint32_t sel_b32(uint32_t a, uint32_t b, uint32_t on) {
-  uint32_t d;
-  asm("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %3, 0;\n\tselp.b32 %0, %1, %2, p;\n\t}" : "=r"(d) : "r"(a), "r"(b), "r"(on));
-  return d;
-}
-template <int SH>
-__device__ __forceinline__ void skew_stage(uint32_t (&r)[64], uint32_t s) {
-  const uint32_t on = s & SH;
-#pragma unroll
-  for (int i = 0; i < 32 + SH - 1; ++i) r[i] = sel_b32(r[i + SH], r[i], on);
-}
-__device__ __forceinline__ void skew_select(uint32_t (&r)[64], int s) {
-  skew_stage<16>(r, s);
-  skew_stage<8>(r, s);
-  skew_stage<4>(r, s);
-  skew_stage<2>(r, s);
-  skew_stage<1>(r, s);
-}
 
 template <int DH>
 __global__ void __launch_bounds__(FA_THREADS, 2)
@@ -305,15 +282,6 @@ static int launch_fwd(const CUtensorMap& tq, const CUtensorMap& tk, const CUtens
   return 0;
 }
 
-static int qkv_map(CUtensorMap* m, const void* base, int dh, int H, int L, int B, int64_t sh, int64_t si,
-                   int64_t sb, int rows) {
-  const uint64_t dims[4] = {static_cast<uint64_t>(dh), static_cast<uint64_t>(H), static_cast<uint64_t>(L),
-                            static_cast<uint64_t>(B)};
-  const uint64_t strides[3] = {static_cast<uint64_t>(sh), static_cast<uint64_t>(si), static_cast<uint64_t>(sb)};
-  const uint32_t box[4] = {64, 1, static_cast<uint32_t>(rows), 1};
-  return make_tmap_nd_bf16(m, base, 4, dims, strides, box);
-}
-
 int launch_attn_fwd_tc(const me_attn_args* a) {
   ME_CHECK(me_device_is_sm100(), "me_attention_forward: the tensor-core path needs an sm_100 device");
   ME_CHECK(a->dtype == ME_BF16, "me_attention_forward: ME_ATTN_TENSOR computes in bf16 only");
@@ -345,11 +313,6 @@ int launch_attn_fwd_tc(const me_attn_args* a) {
   if (a->dh == 64) return launch_fwd<64>(tq, tk, tv, te, p, grid, st);
   if (a->dh == 48) return launch_fwd<48>(tq, tk, tv, te, p, grid, st);
   return launch_fwd<32>(tq, tk, tv, te, p, grid, st);
-}
-
-int launch_attn_bwd_tc(const me_attn_bwd_args*) {
-  set_error("me_attention_backward: ME_ATTN_TENSOR backward is not built in this version");
-  return 1;
 }
 
 }  // namespace me

@@ -180,6 +180,7 @@ extern "C" int me_layer_backward(const me_layer_bwd_args* b) {
   t.dv = offs(b->g_qkv, dt, 2 * d);
   t.dE = b->dE;
   t.dsum = b->dsum;
+  t.dq_acc = b->g_b;  // free at this point: LayerNorm-1 backward has consumed it
   if (me_attention_backward(&t)) return 1;
 
   if (launch_colsum(b->g_qkv, dt, M, 3 * d, 3 * d, b->dbqkv, st)) return 1;

@@ -152,7 +152,9 @@ class MusicTransformer(nn.Module):
             return _lib.ATTN_SIMT
         if self.attn_impl == "tensor":
             return _lib.ATTN_TENSOR
-        return _lib.ATTN_TENSOR if (dtype == ME_BF16 and _TENSOR_ATTENTION_AVAILABLE) else _lib.ATTN_SIMT
+        dh = self.embedding_dim // self.num_head
+        ok = dtype == ME_BF16 and _TENSOR_ATTENTION_AVAILABLE and dh in (32, 48, 64)
+        return _lib.ATTN_TENSOR if ok else _lib.ATTN_SIMT
 
     def invalidate_weight_cache(self):
         self._wcache.clear()
@@ -240,7 +242,7 @@ class MusicTransformer(nn.Module):
                 f"continuous_token={self.continuous_token}, dropout={self.dropout_p}")
 
 
-_TENSOR_ATTENTION_AVAILABLE = False
+_TENSOR_ATTENTION_AVAILABLE = True
 
 
 def set_dropout(model: MusicTransformer, rate: float) -> MusicTransformer:

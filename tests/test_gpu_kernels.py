@@ -350,3 +350,58 @@ def test_attention_tensor_core_forward(B, H, L, dh, pad):
     out2, lse2, _ = _run_attention_forward(_lib.ATTN_SIMT, qkv, E, keypad if pad else None, B, H, L, dh)
     assert torch.allclose(lse, lse2, rtol=1e-3, atol=2e-3), (lse - lse2).abs().max()
     assert rel_err(out.float(), out2.float()) < 8e-3
+
+
+def _run_attention_backward(impl, a, qkv, out, lse, dout, B, H, L, dh):
+    d = H * dh
+    es = qkv.element_size()
+    g_qkv = torch.full_like(qkv, float("nan"))
+    dE = torch.zeros(2048, dh, device="cuda")
+    dsum = torch.empty(B, H, L, device="cuda")
+    dq_acc = torch.empty(B, L, d, device="cuda")
+    ba = _lib.AttnBwdArgs()
+    ba.f = a
+    ba.f.impl = impl
+    ba.f.out, ba.f.lse = out.data_ptr(), lse.data_ptr()
+    ba.dout = dout.data_ptr()
+    ba.dq, ba.dk, ba.dv = g_qkv.data_ptr(), g_qkv.data_ptr() + d * es, g_qkv.data_ptr() + 2 * d * es
+    ba.dE, ba.dsum, ba.dq_acc = dE.data_ptr(), dsum.data_ptr(), dq_acc.data_ptr()
+    _lib.call("me_attention_backward", C.byref(ba))
+    return g_qkv, dE
+
+
+@pytest.mark.parametrize("B,H,L,dh", [(2, 2, 37, 48), (1, 3, 130, 64), (2, 1, 64, 32), (2, 2, 300, 64),
+                                      (1, 2, 1024, 64), (1, 1, 2048, 64), (2, 4, 1026, 48)])
+@pytest.mark.parametrize("pad", [False, True])
+def test_attention_tensor_core_backward(B, H, L, dh, pad):
+    MS = 2048
+    d = H * dh
+    g = torch.Generator(device="cuda").manual_seed(L * 3 + dh)
+    qkv = (torch.randn(B, L, 3, H, dh, device="cuda", generator=g) * 0.8).to(torch.bfloat16)
+    E = (torch.randn(MS, dh, device="cuda", generator=g) * 0.3).to(torch.bfloat16)
+    keypad = torch.zeros(B, L, device="cuda", dtype=torch.uint8)
+    if pad:
+        keypad[0, L - min(L // 3, 70):] = 1
+        keypad[B - 1, 1::5] = 1
+    kp = keypad if pad else None
+    out, lse, a = _run_attention_forward(_lib.ATTN_TENSOR, qkv, E, kp, B, H, L, dh)
+    dout = torch.randn(B, L, d, device="cuda", generator=g).to(torch.bfloat16)
+    g_tc, dE_tc = _run_attention_backward(_lib.ATTN_TENSOR, a, qkv, out, lse, dout, B, H, L, dh)
+    torch.cuda.synchronize()
+    assert torch.isfinite(g_tc.float()).all() and torch.isfinite(dE_tc).all()
+
+    q = qkv[:, :, 0].permute(0, 2, 1, 3).float().requires_grad_(True)
+    k = qkv[:, :, 1].permute(0, 2, 1, 3).float().requires_grad_(True)
+    v = qkv[:, :, 2].permute(0, 2, 1, 3).float().requires_grad_(True)
+    Er = E.float().requires_grad_(True)
+    want = _attn_reference(q, k, v, Er, keypad, MS).permute(0, 2, 1, 3).reshape(B, L, d)
+    want.backward(dout.double())
+    tol = 1.5e-2
+    assert rel_err(g_tc[:, :, 0].permute(0, 2, 1, 3).float(), q.grad) < tol
+    assert rel_err(g_tc[:, :, 1].permute(0, 2, 1, 3).float(), k.grad) < tol
+    assert rel_err(g_tc[:, :, 2].permute(0, 2, 1, 3).float(), v.grad) < tol
+    assert rel_err(dE_tc, Er.grad) < tol
+    # and against the SIMT backward on the same saved forward
+    g_si, dE_si = _run_attention_backward(_lib.ATTN_SIMT, a, qkv, out, lse, dout, B, H, L, dh)
+    assert rel_err(g_tc.float(), g_si.float()) < tol
+    assert rel_err(dE_tc, dE_si) < tol
