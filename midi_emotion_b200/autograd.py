@@ -51,9 +51,14 @@ def _layer_args(model, wl: dict, lay, act: dict, x_f32, x_T, keypad, a: _Acts, l
     return la
 
 
-def run_forward(model, tokens: torch.Tensor, cond: Optional[torch.Tensor], need_grad: bool):
-    """Enqueue the forward pass.  Returns (logits_padded [M, Vp] in compute type, acts)."""
-    dtype = model._resolve_dtype()
+def run_forward(model, tokens: torch.Tensor, cond: Optional[torch.Tensor], need_grad: bool, dtype=None,
+                kv_sink=None, last_only: bool = False):
+    """Enqueue the forward pass.  Returns (logits_padded [M, Vp] in compute type, acts).
+
+    kv_sink(layer_index, qkv[M, 3d]) is called after every layer (KV-cache prefill);
+    last_only computes the output head for the last position of every sequence only ([B, Vp])."""
+    if dtype is None:
+        dtype = model._resolve_dtype()
     tdt = _tdtype(dtype)
     dev = tokens.device
     B, L = tokens.shape
@@ -108,6 +113,8 @@ def run_forward(model, tokens: torch.Tensor, cond: Optional[torch.Tensor], need_
             la.training = 1  # keep the statistics needed by backward even when dropout is off
             la.dropout_p = a.p
         _lib.call("me_layer_forward", C.byref(la))
+        if kv_sink is not None:
+            kv_sink(l, act["qkv"])
         x_f32, x_T = act["out2_f32"], act["out2_T"]
         if need_grad:
             act.pop("proj", None)
@@ -118,6 +125,9 @@ def run_forward(model, tokens: torch.Tensor, cond: Optional[torch.Tensor], need_
     # output head (music_multi.py:106): logits[M, V]; rows padded to Vp so that they stay 16-byte aligned
     Vp = (V + 7) // 8 * 8
     a.Vp = Vp
+    if last_only:
+        x_T = x_T.view(B, Ls, d)[:, -1, :].contiguous()
+        M = B
     logits = torch.empty(M, Vp, **tt)
     if Vp != V:
         logits[:, V:].zero_()

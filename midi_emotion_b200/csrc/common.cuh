@@ -73,20 +73,45 @@ template <typename T> __device__ __forceinline__ T from_f32(float v);
 template <> __device__ __forceinline__ float from_f32<float>(float v) { return v; }
 template <> __device__ __forceinline__ bf16 from_f32<bf16>(float v) { return __float2bfloat16_rn(v); }
 
-// Stateless dropout RNG: splitmix64 finaliser over (seed, element index).  The same
-// (seed, index) pair regenerates the same keep decision in the backward pass.
-__device__ __forceinline__ uint32_t hash_u32(uint64_t seed, uint64_t idx) {
-  uint64_t z = seed + idx * 0x9E3779B97F4A7C15ull;
-  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
-  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
-  z ^= z >> 31;
-  return static_cast<uint32_t>(z >> 32);
+// Stateless dropout RNG.  One 32-bit hash (murmur3 finaliser over a Weyl-scrambled index) yields the
+// keep decisions of two neighbouring elements (16 bits each, threshold resolution 2^-16).  The same
+// (seed, index) pair regenerates the same decision in the backward pass.
+__device__ __forceinline__ uint32_t mix32(uint32_t h) {
+  h ^= h >> 16;
+  h *= 0x85EBCA6Bu;
+  h ^= h >> 13;
+  h *= 0xC2B2AE35u;
+  h ^= h >> 16;
+  return h;
 }
-// returns the multiplier applied to an activation: 0 (dropped) or 1/(1-p)
+__device__ __forceinline__ uint32_t dropout_seed32(uint64_t seed) {
+  return mix32(static_cast<uint32_t>(seed) ^ (static_cast<uint32_t>(seed >> 32) * 0x9E3779B1u));
+}
+// hash shared by elements idx (even) and idx + 1
+__device__ __forceinline__ uint32_t dropout_pair_hash(uint32_t seed32, uint64_t idx) {
+  const uint32_t pair = static_cast<uint32_t>(idx >> 1) + static_cast<uint32_t>(idx >> 33) * 0x7F4A7C15u;
+  return mix32(pair * 0x9E3779B1u + seed32);
+}
+__device__ __forceinline__ uint32_t dropout_threshold(float p) { return static_cast<uint32_t>(p * 65536.f); }
+// multiplier applied to an activation: 0 (dropped) or 1/(1-p)
 __device__ __forceinline__ float dropout_scale(float p, float inv_keep, uint64_t seed, uint64_t idx) {
   if (p <= 0.f) return 1.f;
-  const uint32_t thr = static_cast<uint32_t>(p * 4294967296.0);
-  return hash_u32(seed, idx) >= thr ? inv_keep : 0.f;
+  const uint32_t h = dropout_pair_hash(dropout_seed32(seed), idx);
+  const uint32_t r = (idx & 1) ? (h >> 16) : (h & 0xFFFFu);
+  return r >= dropout_threshold(p) ? inv_keep : 0.f;
+}
+// four consecutive elements starting at idx (idx % 4 == 0)
+__device__ __forceinline__ void dropout_scale4(float p, float inv_keep, uint32_t seed32, uint64_t idx, float (&m)[4]) {
+  if (p <= 0.f) {
+    m[0] = m[1] = m[2] = m[3] = 1.f;
+    return;
+  }
+  const uint32_t thr = dropout_threshold(p);
+  const uint32_t h0 = dropout_pair_hash(seed32, idx), h1 = dropout_pair_hash(seed32, idx + 2);
+  m[0] = (h0 & 0xFFFFu) >= thr ? inv_keep : 0.f;
+  m[1] = (h0 >> 16) >= thr ? inv_keep : 0.f;
+  m[2] = (h1 & 0xFFFFu) >= thr ? inv_keep : 0.f;
+  m[3] = (h1 >> 16) >= thr ? inv_keep : 0.f;
 }
 
 // ---------------------------------------------------------------------------------

@@ -119,149 +119,242 @@ __global__ void embed_bwd_kernel(const float* __restrict__ dx, const int64_t* __
 }
 
 // =====================================================================================
-// out = LayerNorm(x_res + dropout(y)),  one warp per row, row staged in shared memory
-// (music_multi.py:128-129,133-134).  Statistics two-pass in fp32 (mean, then biased variance).
+// out = LayerNorm(x_res + dropout(y))   (music_multi.py:128-129,133-134; eps 1e-6)
+// One warp per row, the row lives in registers as float4 chunks (lane l owns columns 4*(l + 32k)..+3),
+// two-pass statistics in fp32 (mean, then biased variance), 16-byte global accesses throughout.
 // =====================================================================================
-constexpr int LN_WARPS = 4;
+constexpr int LN_THREADS = 256;
 
-template <typename T>
-__global__ void add_ln_fwd_kernel(const float* __restrict__ x_res, const T* __restrict__ y,
-                                  const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
-                                  int M, int d, float p, uint64_t seed, float* __restrict__ out_f32,
-                                  T* __restrict__ out_T, float* __restrict__ zsave, float* __restrict__ mean_out,
-                                  float* __restrict__ rstd_out) {
-  extern __shared__ float ln_smem[];
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int64_t row = static_cast<int64_t>(blockIdx.x) * LN_WARPS + warp;
-  if (row >= M) return;
-  float* zr = ln_smem + warp * d;
+template <typename T> struct Vec4 {};
+template <> struct Vec4<float> {
+  static __device__ __forceinline__ void load(const float* p, float (&v)[4]) {
+    const float4 t = *reinterpret_cast<const float4*>(p);
+    v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+  }
+  static __device__ __forceinline__ void store(float* p, const float (&v)[4]) {
+    *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+  }
+};
+template <> struct Vec4<bf16> {
+  static __device__ __forceinline__ void load(const bf16* p, float (&v)[4]) {
+    const uint2 u = *reinterpret_cast<const uint2*>(p);
+    const float2 a = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u.x));
+    const float2 b = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u.y));
+    v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y;
+  }
+  static __device__ __forceinline__ void store(bf16* p, const float (&v)[4]) {
+    __nv_bfloat162 a = __floats2bfloat162_rn(v[0], v[1]), b = __floats2bfloat162_rn(v[2], v[3]);
+    uint2 u;
+    u.x = *reinterpret_cast<uint32_t*>(&a);
+    u.y = *reinterpret_cast<uint32_t*>(&b);
+    *reinterpret_cast<uint2*>(p) = u;
+  }
+};
+
+template <typename T, int NCH>
+__global__ void __launch_bounds__(LN_THREADS)
+add_ln_fwd_kernel(const float* __restrict__ x_res, const T* __restrict__ y, const float* __restrict__ gamma,
+                  const float* __restrict__ beta, float eps, int M, int d, float p, uint64_t seed,
+                  float* __restrict__ out_f32, T* __restrict__ out_T, float* __restrict__ zsave,
+                  float* __restrict__ mean_out, float* __restrict__ rstd_out) {
+  const int lane = threadIdx.x & 31;
+  const int wpb = LN_THREADS / 32;
+  const int64_t warp0 = static_cast<int64_t>(blockIdx.x) * wpb + (threadIdx.x >> 5);
+  const int64_t nwarps = static_cast<int64_t>(gridDim.x) * wpb;
   const float inv_keep = p > 0.f ? 1.f / (1.f - p) : 1.f;
-  float sum = 0.f;
-  for (int c = lane; c < d; c += 32) {
-    const int64_t idx = row * d + c;
-    float yv = to_f32<T>(y[idx]);
-    yv *= dropout_scale(p, inv_keep, seed, static_cast<uint64_t>(idx));
-    const float z = yv + x_res[idx];
-    zr[c] = z;
-    sum += z;
+  const uint32_t seed32 = dropout_seed32(seed);
+  const float inv_d = 1.f / static_cast<float>(d);
+  const bool alias = static_cast<const void*>(out_T) == static_cast<const void*>(out_f32);
+  float gam[NCH][4], bet[NCH][4];
+#pragma unroll
+  for (int k = 0; k < NCH; ++k) {
+    const int c = 4 * (lane + 32 * k);
+    if (c < d) {
+      Vec4<float>::load(gamma + c, gam[k]);
+      Vec4<float>::load(beta + c, bet[k]);
+    }
   }
-  const float mean = warp_sum(sum) / d;
-  float vs = 0.f;
-  for (int c = lane; c < d; c += 32) {
-    const float dz = zr[c] - mean;
-    vs += dz * dz;
-  }
-  const float rstd = 1.f / sqrtf(warp_sum(vs) / d + eps);
-  if (lane == 0) {
-    if (mean_out) mean_out[row] = mean;
-    if (rstd_out) rstd_out[row] = rstd;
-  }
-  const bool alias = static_cast<void*>(out_T) == static_cast<void*>(out_f32);
-  for (int c = lane; c < d; c += 32) {
-    const int64_t idx = row * d + c;
-    const float z = zr[c];
-    const float o = (z - mean) * rstd * gamma[c] + beta[c];
-    if (zsave) zsave[idx] = z;
-    out_f32[idx] = o;
-    if (out_T != nullptr && !alias) out_T[idx] = from_f32<T>(o);
+  for (int64_t row = warp0; row < M; row += nwarps) {
+    float z[NCH][4];
+    float sum = 0.f;
+#pragma unroll
+    for (int k = 0; k < NCH; ++k) {
+      const int c = 4 * (lane + 32 * k);
+      if (c < d) {
+        const int64_t idx = row * d + c;
+        float yv[4], xv[4], dm[4];
+        Vec4<T>::load(y + idx, yv);
+        Vec4<float>::load(x_res + idx, xv);
+        dropout_scale4(p, inv_keep, seed32, static_cast<uint64_t>(idx), dm);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          z[k][e] = yv[e] * dm[e] + xv[e];
+          sum += z[k][e];
+        }
+      }
+    }
+    const float mean = warp_sum(sum) * inv_d;
+    float vs = 0.f;
+#pragma unroll
+    for (int k = 0; k < NCH; ++k) {
+      if (4 * (lane + 32 * k) < d) {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const float dz = z[k][e] - mean;
+          vs += dz * dz;
+        }
+      }
+    }
+    const float rstd = 1.f / sqrtf(warp_sum(vs) * inv_d + eps);
+    if (lane == 0) {
+      if (mean_out) mean_out[row] = mean;
+      if (rstd_out) rstd_out[row] = rstd;
+    }
+#pragma unroll
+    for (int k = 0; k < NCH; ++k) {
+      const int c = 4 * (lane + 32 * k);
+      if (c < d) {
+        const int64_t idx = row * d + c;
+        float o[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) o[e] = (z[k][e] - mean) * rstd * gam[k][e] + bet[k][e];
+        if (zsave) Vec4<float>::store(zsave + idx, z[k]);
+        Vec4<float>::store(out_f32 + idx, o);
+        if (out_T != nullptr && !alias) Vec4<T>::store(out_T + idx, o);
+      }
+    }
   }
 }
 
-// LayerNorm backward.  Each block owns a contiguous chunk of rows; every lane keeps the partial
-// d_gamma / d_beta sums of its own columns (c = lane + 32k) in registers across the rows its warp
-// visits, the warps combine through shared memory and flush one atomicAdd per column per block.
-template <typename T, int KMAX>
-__global__ void add_ln_bwd_kernel(const float* __restrict__ dout, const float* __restrict__ dout_add,
-                                  const float* __restrict__ z, const float* __restrict__ mean,
-                                  const float* __restrict__ rstd, const float* __restrict__ gamma, int M, int d,
-                                  int rows_per_block, float p, uint64_t seed, float* __restrict__ dz_f32,
-                                  T* __restrict__ dy_T, float* __restrict__ d_gamma,
-                                  float* __restrict__ d_beta) {
-  extern __shared__ float ln_smem[];
-  float* dg_s = ln_smem;        // [d]
-  float* db_s = ln_smem + d;    // [d]
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  for (int c = threadIdx.x; c < d; c += blockDim.x) {
-    dg_s[c] = 0.f;
-    db_s[c] = 0.f;
-  }
+// LayerNorm backward.  Persistent warps walk the rows; every lane keeps the partial d_gamma / d_beta
+// (and, optionally, the column sums of the masked dy = bias gradient of the preceding Linear) of its
+// own columns in registers, the warps of a block combine through shared memory and flush one
+// atomicAdd per column per block.
+template <typename T, int NCH>
+__global__ void __launch_bounds__(LN_THREADS)
+add_ln_bwd_kernel(const float* __restrict__ dout, const float* __restrict__ dout_add, const float* __restrict__ z,
+                  const float* __restrict__ mean, const float* __restrict__ rstd, const float* __restrict__ gamma,
+                  int M, int d, float p, uint64_t seed, float* __restrict__ dz_f32, T* __restrict__ dy_T,
+                  float* __restrict__ d_gamma, float* __restrict__ d_beta, float* __restrict__ d_ybias) {
+  extern __shared__ float ln_smem[];  // [3][d]
+  const int lane = threadIdx.x & 31;
+  const int wpb = LN_THREADS / 32;
+  const int64_t warp0 = static_cast<int64_t>(blockIdx.x) * wpb + (threadIdx.x >> 5);
+  const int64_t nwarps = static_cast<int64_t>(gridDim.x) * wpb;
+  for (int c = threadIdx.x; c < 3 * d; c += LN_THREADS) ln_smem[c] = 0.f;
   __syncthreads();
-  float dg[KMAX], db[KMAX], gam[KMAX];
-#pragma unroll
-  for (int k = 0; k < KMAX; ++k) {
-    dg[k] = 0.f;
-    db[k] = 0.f;
-    const int c = lane + 32 * k;
-    gam[k] = c < d ? gamma[c] : 0.f;
-  }
   const float inv_keep = p > 0.f ? 1.f / (1.f - p) : 1.f;
-  const int64_t r0 = static_cast<int64_t>(blockIdx.x) * rows_per_block;
-  const int64_t r1 = min(static_cast<int64_t>(M), r0 + rows_per_block);
-  const bool alias = static_cast<void*>(dy_T) == static_cast<void*>(dz_f32);
-  for (int64_t row = r0 + warp; row < r1; row += LN_WARPS) {
+  const uint32_t seed32 = dropout_seed32(seed);
+  const float inv_d = 1.f / static_cast<float>(d);
+  const bool alias = static_cast<const void*>(dy_T) == static_cast<const void*>(dz_f32);
+  float gam[NCH][4], dg[NCH][4], db[NCH][4], dyb[NCH][4];
+#pragma unroll
+  for (int k = 0; k < NCH; ++k) {
+    const int c = 4 * (lane + 32 * k);
+#pragma unroll
+    for (int e = 0; e < 4; ++e) dg[k][e] = db[k][e] = dyb[k][e] = gam[k][e] = 0.f;
+    if (c < d) Vec4<float>::load(gamma + c, gam[k]);
+  }
+  for (int64_t row = warp0; row < M; row += nwarps) {
     const float mu = mean[row], rs = rstd[row];
-    float dyv[KMAX], xh[KMAX];
+    float dy[NCH][4], xh[NCH][4];
     float s1 = 0.f, s2 = 0.f;
 #pragma unroll
-    for (int k = 0; k < KMAX; ++k) {
-      const int c = lane + 32 * k;
-      dyv[k] = 0.f;
-      xh[k] = 0.f;
+    for (int k = 0; k < NCH; ++k) {
+      const int c = 4 * (lane + 32 * k);
       if (c < d) {
         const int64_t idx = row * d + c;
-        float dy = dout[idx];
-        if (dout_add) dy += dout_add[idx];
-        dyv[k] = dy;
-        xh[k] = (z[idx] - mu) * rs;
-        const float g = dy * gam[k];
-        s1 += g;
-        s2 += g * xh[k];
-        dg[k] += dy * xh[k];
-        db[k] += dy;
+        float zv[4];
+        Vec4<float>::load(dout + idx, dy[k]);
+        Vec4<float>::load(z + idx, zv);
+        if (dout_add) {
+          float t[4];
+          Vec4<float>::load(dout_add + idx, t);
+#pragma unroll
+          for (int e = 0; e < 4; ++e) dy[k][e] += t[e];
+        }
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          xh[k][e] = (zv[e] - mu) * rs;
+          const float g = dy[k][e] * gam[k][e];
+          s1 += g;
+          s2 += g * xh[k][e];
+          dg[k][e] += dy[k][e] * xh[k][e];
+          db[k][e] += dy[k][e];
+        }
       }
     }
-    s1 = warp_sum(s1) / d;
-    s2 = warp_sum(s2) / d;
+    s1 = warp_sum(s1) * inv_d;
+    s2 = warp_sum(s2) * inv_d;
 #pragma unroll
-    for (int k = 0; k < KMAX; ++k) {
-      const int c = lane + 32 * k;
+    for (int k = 0; k < NCH; ++k) {
+      const int c = 4 * (lane + 32 * k);
       if (c < d) {
         const int64_t idx = row * d + c;
-        const float dzv = rs * (dyv[k] * gam[k] - s1 - xh[k] * s2);
-        if (dz_f32) dz_f32[idx] = dzv;
-        if (dy_T != nullptr && !alias)
-          dy_T[idx] = from_f32<T>(dzv * dropout_scale(p, inv_keep, seed, static_cast<uint64_t>(idx)));
+        float dzv[4], dm[4], dyv[4];
+        dropout_scale4(p, inv_keep, seed32, static_cast<uint64_t>(idx), dm);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          dzv[e] = rs * (dy[k][e] * gam[k][e] - s1 - xh[k][e] * s2);
+          dyv[e] = dzv[e] * dm[e];
+          dyb[k][e] += dyv[e];
+        }
+        if (dz_f32) Vec4<float>::store(dz_f32 + idx, dzv);
+        if (dy_T != nullptr && !alias) Vec4<T>::store(dy_T + idx, dyv);
       }
     }
   }
 #pragma unroll
-  for (int k = 0; k < KMAX; ++k) {
-    const int c = lane + 32 * k;
+  for (int k = 0; k < NCH; ++k) {
+    const int c = 4 * (lane + 32 * k);
     if (c < d) {
-      atomicAdd(&dg_s[c], dg[k]);
-      atomicAdd(&db_s[c], db[k]);
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        atomicAdd(&ln_smem[c + e], dg[k][e]);
+        atomicAdd(&ln_smem[d + c + e], db[k][e]);
+        atomicAdd(&ln_smem[2 * d + c + e], dyb[k][e]);
+      }
     }
   }
   __syncthreads();
-  for (int c = threadIdx.x; c < d; c += blockDim.x) {
-    atomicAdd(&d_gamma[c], dg_s[c]);
-    atomicAdd(&d_beta[c], db_s[c]);
+  for (int c = threadIdx.x; c < d; c += LN_THREADS) {
+    atomicAdd(&d_gamma[c], ln_smem[c]);
+    atomicAdd(&d_beta[c], ln_smem[d + c]);
+    if (d_ybias) atomicAdd(&d_ybias[c], ln_smem[2 * d + c]);
   }
 }
 
 // =====================================================================================
-// column sums (bias gradients)
+// column sums (bias gradients): 8 columns per thread (16-byte loads), rows split over blockIdx.y
 // =====================================================================================
 template <typename T>
 __global__ void colsum_kernel(const T* __restrict__ X, int M, int N, int ldx, int rows_per_block,
                               float* __restrict__ out) {
-  const int n = blockIdx.x * blockDim.x + threadIdx.x;
-  if (n >= N) return;
+  constexpr int VEC = 16 / sizeof(T);
+  const int n0 = (blockIdx.x * blockDim.x + threadIdx.x) * VEC;
+  if (n0 >= N) return;
   const int64_t r0 = static_cast<int64_t>(blockIdx.y) * rows_per_block;
   const int64_t r1 = min(static_cast<int64_t>(M), r0 + rows_per_block);
-  float acc = 0.f;
-  for (int64_t r = r0; r < r1; ++r) acc += to_f32<T>(X[r * ldx + n]);
-  atomicAdd(&out[n], acc);
+  float acc[VEC];
+#pragma unroll
+  for (int e = 0; e < VEC; ++e) acc[e] = 0.f;
+  const bool vec_ok = (n0 + VEC <= N) && (ldx % VEC == 0) && ((reinterpret_cast<uintptr_t>(X) & 15) == 0);
+  if (vec_ok) {
+#pragma unroll 4
+    for (int64_t r = r0; r < r1; ++r) {
+      const uint4 u = *reinterpret_cast<const uint4*>(X + r * ldx + n0);
+      const T* v = reinterpret_cast<const T*>(&u);
+#pragma unroll
+      for (int e = 0; e < VEC; ++e) acc[e] += to_f32<T>(v[e]);
+    }
+  } else {
+    for (int64_t r = r0; r < r1; ++r)
+      for (int e = 0; e < VEC; ++e)
+        if (n0 + e < N) acc[e] += to_f32<T>(X[r * ldx + n0 + e]);
+  }
+#pragma unroll
+  for (int e = 0; e < VEC; ++e)
+    if (n0 + e < N) atomicAdd(&out[n0 + e], acc[e]);
 }
 
 template <typename TS, typename TD>
@@ -333,61 +426,98 @@ int launch_embed(const int64_t* tokens, const float* cond, const float* emb_w, c
   return 0;
 }
 
+template <typename T>
+static int ln_fwd_dispatch(int nch, int blocks, cudaStream_t st, const float* x_res, const T* y, const float* gamma,
+                           const float* beta, float eps, int M, int d, float p, uint64_t seed, float* out_f32,
+                           T* out_T, float* z, float* mean, float* rstd) {
+#define ME_LN_FWD(N)                                                                                        \
+  add_ln_fwd_kernel<T, N><<<blocks, LN_THREADS, 0, st>>>(x_res, y, gamma, beta, eps, M, d, p, seed, out_f32, \
+                                                         out_T, z, mean, rstd)
+  switch (nch) {
+    case 1: ME_LN_FWD(1); break;
+    case 2: ME_LN_FWD(2); break;
+    case 3: ME_LN_FWD(3); break;
+    case 4: ME_LN_FWD(4); break;
+    case 6: ME_LN_FWD(6); break;
+    case 8: ME_LN_FWD(8); break;
+    default: ME_LN_FWD(8); break;
+  }
+#undef ME_LN_FWD
+  return 0;
+}
+
+static int ln_nch(int d) {
+  const int n = (d + 127) / 128;
+  if (n <= 4) return n;
+  if (n <= 6) return 6;
+  return 8;
+}
+
 int launch_add_ln_fwd(const float* x_res, const void* y, int dtype, const float* gamma, const float* beta,
                       float eps, int M, int d, float p, uint64_t seed, float* out_f32, void* out_T, float* z,
                       float* mean, float* rstd, cudaStream_t st) {
-  const int blocks = (M + LN_WARPS - 1) / LN_WARPS;
-  const size_t smem = static_cast<size_t>(LN_WARPS) * d * sizeof(float);
+  ME_CHECK(d % 4 == 0 && d <= 1024, "layernorm: d=%d must be a multiple of 4 and <= 1024", d);
+  const int wpb = LN_THREADS / 32;
+  int blocks = (M + wpb - 1) / wpb;
+  const int cap = sm_count() * 8;
+  if (blocks > cap) blocks = cap;
   if (dtype == ME_BF16)
-    add_ln_fwd_kernel<bf16><<<blocks, LN_WARPS * 32, smem, st>>>(x_res, static_cast<const bf16*>(y), gamma, beta,
-                                                                 eps, M, d, p, seed, out_f32,
-                                                                 static_cast<bf16*>(out_T), z, mean, rstd);
+    ln_fwd_dispatch<bf16>(ln_nch(d), blocks, st, x_res, static_cast<const bf16*>(y), gamma, beta, eps, M, d, p, seed,
+                          out_f32, static_cast<bf16*>(out_T), z, mean, rstd);
   else
-    add_ln_fwd_kernel<float><<<blocks, LN_WARPS * 32, smem, st>>>(x_res, static_cast<const float*>(y), gamma, beta,
-                                                                  eps, M, d, p, seed, out_f32,
-                                                                  static_cast<float*>(out_T), z, mean, rstd);
+    ln_fwd_dispatch<float>(ln_nch(d), blocks, st, x_res, static_cast<const float*>(y), gamma, beta, eps, M, d, p,
+                           seed, out_f32, static_cast<float*>(out_T), z, mean, rstd);
   ME_LAUNCH_CHECK();
+  return 0;
+}
+
+template <typename T>
+static int ln_bwd_dispatch(int nch, int blocks, size_t smem, cudaStream_t st, const float* dout,
+                           const float* dout_add, const float* z, const float* mean, const float* rstd,
+                           const float* gamma, int M, int d, float p, uint64_t seed, float* dz_f32, T* dy_T,
+                           float* d_gamma, float* d_beta, float* d_ybias) {
+#define ME_LN_BWD(N)                                                                                           \
+  add_ln_bwd_kernel<T, N><<<blocks, LN_THREADS, smem, st>>>(dout, dout_add, z, mean, rstd, gamma, M, d, p, seed, \
+                                                            dz_f32, dy_T, d_gamma, d_beta, d_ybias)
+  switch (nch) {
+    case 1: ME_LN_BWD(1); break;
+    case 2: ME_LN_BWD(2); break;
+    case 3: ME_LN_BWD(3); break;
+    case 4: ME_LN_BWD(4); break;
+    case 6: ME_LN_BWD(6); break;
+    case 8: ME_LN_BWD(8); break;
+    default: ME_LN_BWD(8); break;
+  }
+#undef ME_LN_BWD
   return 0;
 }
 
 int launch_add_ln_bwd(const float* dout, const float* dout_add, const float* z, const float* mean,
                       const float* rstd, const float* gamma, int M, int d, float p, uint64_t seed, int dtype,
-                      float* dz_f32, void* dy_T, float* d_gamma, float* d_beta, cudaStream_t st) {
-  int blocks = sm_count() * 4;
-  int rpb = (M + blocks - 1) / blocks;
-  rpb = ((rpb + LN_WARPS - 1) / LN_WARPS) * LN_WARPS;
-  if (rpb < LN_WARPS) rpb = LN_WARPS;
-  blocks = (M + rpb - 1) / rpb;
-  const size_t smem = 2 * static_cast<size_t>(d) * sizeof(float);
-#define ME_LN_BWD(KM)                                                                                          \
-  do {                                                                                                         \
-    if (dtype == ME_BF16)                                                                                      \
-      add_ln_bwd_kernel<bf16, KM><<<blocks, LN_WARPS * 32, smem, st>>>(dout, dout_add, z, mean, rstd, gamma, M, \
-                                                                       d, rpb, p, seed, dz_f32,                \
-                                                                       static_cast<bf16*>(dy_T), d_gamma, d_beta); \
-    else                                                                                                       \
-      add_ln_bwd_kernel<float, KM><<<blocks, LN_WARPS * 32, smem, st>>>(dout, dout_add, z, mean, rstd, gamma, M, \
-                                                                        d, rpb, p, seed, dz_f32,               \
-                                                                        static_cast<float*>(dy_T), d_gamma, d_beta); \
-  } while (0)
-  if (d <= 128) ME_LN_BWD(4);
-  else if (d <= 256) ME_LN_BWD(8);
-  else if (d <= 512) ME_LN_BWD(16);
-  else if (d <= 768) ME_LN_BWD(24);
-  else if (d <= 1024) ME_LN_BWD(32);
-  else if (d <= 2048) ME_LN_BWD(64);
-  else { set_error("layernorm backward: d=%d > 2048 unsupported", d); return 1; }
-#undef ME_LN_BWD
+                      float* dz_f32, void* dy_T, float* d_gamma, float* d_beta, float* d_ybias, cudaStream_t st) {
+  ME_CHECK(d % 4 == 0 && d <= 1024, "layernorm backward: d=%d must be a multiple of 4 and <= 1024", d);
+  const int wpb = LN_THREADS / 32;
+  int blocks = (M + wpb - 1) / wpb;
+  const int cap = sm_count() * 4;
+  if (blocks > cap) blocks = cap;
+  const size_t smem = 3 * static_cast<size_t>(d) * sizeof(float);
+  if (dtype == ME_BF16)
+    ln_bwd_dispatch<bf16>(ln_nch(d), blocks, smem, st, dout, dout_add, z, mean, rstd, gamma, M, d, p, seed, dz_f32,
+                          static_cast<bf16*>(dy_T), d_gamma, d_beta, d_ybias);
+  else
+    ln_bwd_dispatch<float>(ln_nch(d), blocks, smem, st, dout, dout_add, z, mean, rstd, gamma, M, d, p, seed, dz_f32,
+                           static_cast<float*>(dy_T), d_gamma, d_beta, d_ybias);
   ME_LAUNCH_CHECK();
   return 0;
 }
 
 int launch_colsum(const void* X, int dtype, int M, int N, int ldx, float* out, cudaStream_t st) {
-  const int threads = 128;
-  const int gx = (N + threads - 1) / threads;
-  int gy = max(1, (sm_count() * 4) / gx);
+  const int threads = 64;
+  const int vec = dtype == ME_BF16 ? 8 : 4;
+  const int gx = ((N + vec - 1) / vec + threads - 1) / threads;
+  int gy = max(1, (sm_count() * 16) / gx);
   int rpb = (M + gy - 1) / gy;
-  if (rpb < 32) rpb = 32;
+  if (rpb < 16) rpb = 16;
   gy = (M + rpb - 1) / rpb;
   dim3 grid(gx, gy);
   if (dtype == ME_BF16)
@@ -440,7 +570,7 @@ extern "C" int me_add_layernorm_forward(const float* x_res, const void* y, int d
                                         const float* beta, float eps, int M, int d, float dropout_p,
                                         uint64_t seed, float* out_f32, void* out_T, float* z, float* mean,
                                         float* rstd, void* stream) {
-  ME_CHECK(M > 0 && d > 0 && d <= 8192, "me_add_layernorm_forward: bad dims M=%d d=%d", M, d);
+  ME_CHECK(M > 0 && d > 0 && d <= 1024, "me_add_layernorm_forward: bad dims M=%d d=%d", M, d);
   return launch_add_ln_fwd(x_res, y, dtype, gamma, beta, eps, M, d, dropout_p, seed, out_f32, out_T, z, mean,
                            rstd, static_cast<cudaStream_t>(stream));
 }
@@ -449,9 +579,9 @@ extern "C" int me_add_layernorm_backward(const float* dout, const float* dout_ad
                                          const float* mean, const float* rstd, const float* gamma, int M, int d,
                                          float dropout_p, uint64_t seed, int dtype, float* dz_f32, void* dy_T,
                                          float* d_gamma, float* d_beta, void* stream) {
-  ME_CHECK(M > 0 && d > 0 && d <= 2048, "me_add_layernorm_backward: bad dims");
+  ME_CHECK(M > 0 && d > 0 && d <= 1024, "me_add_layernorm_backward: bad dims");
   return launch_add_ln_bwd(dout, dout_add, z, mean, rstd, gamma, M, d, dropout_p, seed, dtype, dz_f32, dy_T,
-                           d_gamma, d_beta, static_cast<cudaStream_t>(stream));
+                           d_gamma, d_beta, nullptr, static_cast<cudaStream_t>(stream));
 }
 
 extern "C" int me_colsum(const void* X, int dtype, int M, int N, int ldx, float* out, void* stream) {

@@ -16,7 +16,7 @@ int launch_add_ln_fwd(const float* x_res, const void* y, int dtype, const float*
                       float* mean, float* rstd, cudaStream_t st);
 int launch_add_ln_bwd(const float* dout, const float* dout_add, const float* z, const float* mean,
                       const float* rstd, const float* gamma, int M, int d, float p, uint64_t seed, int dtype,
-                      float* dz_f32, void* dy_T, float* d_gamma, float* d_beta, cudaStream_t st);
+                      float* dz_f32, void* dy_T, float* d_gamma, float* d_beta, float* d_ybias, cudaStream_t st);
 int launch_colsum(const void* X, int dtype, int M, int N, int ldx, float* out, cudaStream_t st);
 int launch_kv_write(const void* qkv, int dtype, int B, int Ls, int H, int dh, void* kc, void* vc, int T_max,
                     int pos0, const int32_t* t_dev, cudaStream_t st);
@@ -144,9 +144,8 @@ extern "C" int me_layer_backward(const me_layer_bwd_args* b) {
 
   // ---- FFN block: out2 = LN2(out1 + drop(W2 relu(W1 out1 + b1) + b2))
   if (launch_add_ln_bwd(b->d_out, nullptr, a->z2, a->mean2, a->rstd2, a->ln2_w, M, d, p, s2, dt, b->g_a, b->g_T,
-                        b->dln2_w, b->dln2_b, st))
+                        b->dln2_w, b->dln2_b, b->db2, st))  // db2 = column sums of the masked gradient
     return 1;
-  if (launch_colsum(b->g_T, dt, M, d, d, b->db2, st)) return 1;
   // dW2[d, di] = g_T^T . h
   if (linear(dt, b->g_T, a->h, b->dW2, d, di, M, d, di, di, 1, 1, true, 0, nullptr, nullptr, nullptr, 0, st)) return 1;
   // g_h[M, di] = (g_T . W2) masked by relu
@@ -164,9 +163,8 @@ extern "C" int me_layer_backward(const me_layer_bwd_args* b) {
 
   // ---- attention block: out1 = LN1(x + drop(Wo attn + bo))
   if (launch_add_ln_bwd(b->g_b, nullptr, a->z1, a->mean1, a->rstd1, a->ln1_w, M, d, p, s1, dt, b->g_a, b->g_T,
-                        b->dln1_w, b->dln1_b, st))
+                        b->dln1_w, b->dln1_b, b->dbo, st))
     return 1;
-  if (launch_colsum(b->g_T, dt, M, d, d, b->dbo, st)) return 1;
   if (linear(dt, b->g_T, a->attn_o, b->dWo, d, d, M, d, d, d, 1, 1, true, 0, nullptr, nullptr, nullptr, 0, st))
     return 1;
   if (linear(dt, b->g_T, a->Wo, b->g_o, M, d, d, d, d, d, 0, 1, false, 0, nullptr, nullptr, nullptr, 0, st)) return 1;

@@ -8,3 +8,4 @@ run tcgen05 tests/test_gpu_kernels.py -k "tcgen05 or epilogues or split_k or rej
 run attn_tc tests/test_gpu_kernels.py -k "tensor_core"
 run model_fp32 tests/test_gpu_model.py -k "not bf16"
 run model_bf16 tests/test_gpu_model.py -k "bf16"
+run decode tests/test_gpu_decode.py
