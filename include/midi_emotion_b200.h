@@ -158,8 +158,9 @@ int me_attention_forward(const me_attn_args* a);
 
 /* Backward of the above (full self-attention only, q_pos0 = 0, Lq = Lk).
  *   dout T same addressing as out; dq/dk/dv T with the q/k/v strides; dE f32 [max_seq, dh]
- *   accumulates (+=, caller zeroes); dsum f32 [B,H,Lq] is scratch; dq_acc f32 [B, Lq, H*dh] is
- *   scratch needed by ME_ATTN_TENSOR only (fp32 accumulation of dq across key tiles). */
+ *   accumulates (+=, caller zeroes); dsum f32 [B,H,Lq] is scratch; dq_acc is fp32 scratch needed by
+ *   ME_ATTN_TENSOR only (dq and dE accumulated across key tiles by TMA reduce-add): 16-byte aligned,
+ *   me_attention_backward_workspace_floats(B, H, Lq, dh, max_seq) floats. */
 typedef struct me_attn_bwd_args {
   me_attn_args f;
   const void* dout;
@@ -169,6 +170,7 @@ typedef struct me_attn_bwd_args {
   float* dq_acc;
 } me_attn_bwd_args;
 int me_attention_backward(const me_attn_bwd_args* a);
+int64_t me_attention_backward_workspace_floats(int B, int H, int L, int dh, int max_seq);
 
 /* ---------------------------------------------------------------------------------------
  * One encoder layer (music_multi.py:126-135): attention block + FFN block, post-LN.
@@ -228,6 +230,7 @@ typedef struct me_layer_bwd_args {
   void* g_qkv;          /* T [M, 3d]  */
   void* g_o;            /* T [M, d]   */
   float* dsum;          /* [B, H, Ls] */
+  float* attn_ws;       /* me_attention_backward_workspace_floats(...) floats; ME_ATTN_TENSOR only */
 } me_layer_bwd_args;
 int me_layer_backward(const me_layer_bwd_args* a);
 

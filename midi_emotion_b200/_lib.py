@@ -52,7 +52,7 @@ class LayerArgs(C.Structure):
 
 
 _LAYER_BWD_PTRS = ["d_out", "d_x", "dWqkv", "dbqkv", "dE", "dWo", "dbo", "dln1_w", "dln1_b", "dW1", "db1", "dW2",
-                   "db2", "dln2_w", "dln2_b", "g_a", "g_b", "g_T", "g_h", "g_qkv", "g_o", "dsum"]
+                   "db2", "dln2_w", "dln2_b", "g_a", "g_b", "g_T", "g_h", "g_qkv", "g_o", "dsum", "attn_ws"]
 
 
 class LayerBwdArgs(C.Structure):
@@ -89,6 +89,7 @@ _PROTOS = {
     "me_convert_2d": (C.c_int, [_vp, C.c_int, C.c_int, _vp, C.c_int, C.c_int, C.c_int, C.c_int, _vp]),
     "me_attention_forward": (C.c_int, [C.POINTER(AttnArgs)]),
     "me_attention_backward": (C.c_int, [C.POINTER(AttnBwdArgs)]),
+    "me_attention_backward_workspace_floats": (C.c_int64, [C.c_int] * 5),
     "me_layer_forward": (C.c_int, [C.POINTER(LayerArgs)]),
     "me_layer_backward": (C.c_int, [C.POINTER(LayerBwdArgs)]),
     "me_decode_layer_step": (C.c_int, [C.POINTER(DecodeLayerArgs)]),

@@ -177,6 +177,10 @@ def run_backward(model, tokens, cond, a: _Acts, g_logits: torch.Tensor) -> List[
         "g_h": torch.empty(M, di, **tt), "g_qkv": torch.empty(M, 3 * d, **tt), "g_o": torch.empty(M, d, **tt),
         "dsum": torch.empty(B, H, Ls, **f32), "proj": torch.empty(M, d, **tt),
     }
+    ws["attn_ws"] = None
+    if a.attn_impl == _lib.ATTN_TENSOR:
+        n_ws = _lib.load().me_attention_backward_workspace_floats(B, H, Ls, dh, model.max_seq)
+        ws["attn_ws"] = torch.empty(n_ws, **f32)
     for l in range(model.num_layer - 1, -1, -1):
         lay = model.enc_layers[l]
         act = a.layers[l]
@@ -198,7 +202,7 @@ def run_backward(model, tokens, cond, a: _Acts, g_logits: torch.Tensor) -> List[
         ba.d_out, ba.d_x = ptr(d_x), ptr(d_x)
         for k, t in g.items():
             setattr(ba, k, ptr(t))
-        for k in ("g_a", "g_b", "g_T", "g_h", "g_qkv", "g_o", "dsum"):
+        for k in ("g_a", "g_b", "g_T", "g_h", "g_qkv", "g_o", "dsum", "attn_ws"):
             setattr(ba, k, ptr(ws[k]))
         _lib.call("me_layer_backward", C.byref(ba))
         for i, n in enumerate(("Wq", "Wk", "Wv")):

@@ -23,8 +23,8 @@ namespace me {
 constexpr int FB_BM = 128;            // query rows per step
 constexpr int FB_BN = 64;             // keys per CTA
 constexpr int FB_EROWS = 192;
-constexpr int FB_THREADS = 128;
-constexpr int FB_STG_STRIDE = 272;    // 256 B of fp32 row + 16 B pad: conflict-free 16-byte stores
+constexpr int FB_THREADS = 256;       // 8 warps: warp w and w+4 share TMEM lanes 32*(w&3).. and split the key columns
+constexpr int FB_STG_MAX = 272;       // staging row pitch for dh = 64: (dh + 4) floats
 constexpr int FB_OFF_K = 0;
 constexpr int FB_OFF_V = FB_OFF_K + 8192;
 constexpr int FB_OFF_Q = FB_OFF_V + 8192;
@@ -34,8 +34,8 @@ constexpr int FB_OFF_P = FB_OFF_E + 24576;
 constexpr int FB_OFF_DS = FB_OFF_P + 16384;
 constexpr int FB_OFF_DSB = FB_OFF_DS + 16384;
 constexpr int FB_OFF_STG0 = FB_OFF_DSB + 49152;
-constexpr int FB_OFF_STG1 = FB_OFF_STG0 + 128 * FB_STG_STRIDE;
-constexpr int FB_OFF_BAR = FB_OFF_STG1 + 128 * FB_STG_STRIDE;
+constexpr int FB_OFF_STG1 = FB_OFF_STG0 + 128 * FB_STG_MAX;
+constexpr int FB_OFF_BAR = FB_OFF_STG1 + 128 * FB_STG_MAX;
 constexpr int FB_SMEM = FB_OFF_BAR + 128;
 static_assert(FB_OFF_STG0 % 1024 == 0 && FB_OFF_BAR % 1024 == 0, "tile alignment");
 static_assert(FB_SMEM <= 227 * 1024, "shared memory budget");
@@ -46,22 +46,41 @@ constexpr uint32_t FB_COL_DE_LO = 128, FB_COL_DE_HI = 192;  // alias R once it h
 struct FbParams {
   int B, H, L, max_seq;
   int64_t k_sb, k_sh, k_sj, v_sb, v_sh, v_sj, keypad_ld;
-  int64_t dq_sb, dq_si;  // fp32 dq accumulator [B, L, H*dh] addressing (elements)
   const uint8_t* keypad;
   const float* lse;
   const float* dsum;
-  float* dq_acc;
-  float* dE;
+  float* dq_ws;  // fp32 [B, H, L, dh + 4]: dq accumulated across key tiles (rows padded like the staging rows)
+  float* dE_ws;  // fp32 [max_seq, dh + 4]
   bf16* dk;
   bf16* dv;
   float scale_log2, scale;
 };
+
+// TMEM -> shared staging: NCOLS (multiple of 8) accumulator columns of this thread's lane
+template <int NCOLS>
+__device__ __forceinline__ void stage_row(uint32_t taddr, float* dst) {
+  static_assert(NCOLS % 8 == 0, "column groups of 8");
+  uint32_t v[NCOLS];
+#pragma unroll
+  for (int c0 = 0; c0 < NCOLS; c0 += 8) {
+    uint32_t t[8];
+    tmem_ld8(taddr + c0, t);
+#pragma unroll
+    for (int c = 0; c < 8; ++c) v[c0 + c] = t[c];
+  }
+  tc_wait_ld();
+#pragma unroll
+  for (int c = 0; c < NCOLS; c += 4)
+    *reinterpret_cast<uint4*>(dst + c) = make_uint4(v[c], v[c + 1], v[c + 2], v[c + 3]);
+}
 
 template <int DH>
 __global__ void __launch_bounds__(FB_THREADS, 1)
 attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                    const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmdO,
                    const __grid_constant__ CUtensorMap tmE, FbParams p) {
+  constexpr int STG = (DH + 4) * 4;   // staging / workspace row pitch in bytes (odd multiple of 16)
+  constexpr int HC = DH / 2;          // accumulator columns handled by each of the two threads of a row
   extern __shared__ __align__(1024) uint8_t fb_smem[];
   uint8_t* sK = fb_smem + FB_OFF_K;
   uint8_t* sV = fb_smem + FB_OFF_V;
@@ -73,6 +92,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   uint8_t* sdSb = fb_smem + FB_OFF_DSB;
   uint8_t* stg0 = fb_smem + FB_OFF_STG0;
   uint8_t* stg1 = fb_smem + FB_OFF_STG1;
+  uint8_t* stg2 = sP;  // P / dS are free between MMA 2 and the next step
   uint64_t* bars = reinterpret_cast<uint64_t*>(fb_smem + FB_OFF_BAR);
   uint64_t* kv_full = bars + 0;
   uint64_t* ld_full = bars + 1;
@@ -81,6 +101,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 4);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int half = warp >> 2, quarter = warp & 3;
   const int kt = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
   const int j0 = kt * FB_BN;
   const int nq = (p.L + FB_BM - 1) / FB_BM;
@@ -112,7 +133,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     tma_load_4d(&tmV, kv_full, sV, 0, h, j0, b);
     load_step(0);
   }
-  // dSb starts as zeros; every step rewrites only the 9 chunks around each row's window
+  // dSb starts as zeros; every step rewrites only the chunks around each row's window
   {
     uint4* z = reinterpret_cast<uint4*>(sdSb);
     for (int c = tid; c < 49152 / 16; c += FB_THREADS) z[c] = make_uint4(0, 0, 0, 0);
@@ -134,29 +155,28 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   const uint32_t k_addr = smem_u32(sK), v_addr = smem_u32(sV), q_addr = smem_u32(sQ), do_addr = smem_u32(sdO);
   const uint32_t e_addr = smem_u32(sE), p_addr = smem_u32(sP), ds_addr = smem_u32(sdS), dsb_addr = smem_u32(sdSb);
 
-  const int a = tid;
+  const int a = quarter * 32 + lane;   // query row inside the tile == TMEM lane
   const int shift = 31 - lane;
-  const uint32_t t_lane = tmem_base + (static_cast<uint32_t>(warp * 32) << 16);
+  const uint32_t t_lane = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16);
   const uint8_t* kp = p.keypad ? p.keypad + static_cast<int64_t>(b) * p.keypad_ld : nullptr;
-  uint32_t kp0 = 0, kp1 = 0;  // key-pad bits of this CTA's 64 keys
+  uint32_t kpm = 0;  // key-pad bits of this thread's 32 keys
   if (kp) {
-    const int ja = j0 + lane, jb = j0 + 32 + lane;
-    kp0 = __ballot_sync(0xffffffffu, ja < p.L && kp[ja] != 0);
-    kp1 = __ballot_sync(0xffffffffu, jb < p.L && kp[jb] != 0);
+    const int j = j0 + 32 * half + lane;
+    kpm = __ballot_sync(0xffffffffu, j < p.L && kp[j] != 0);
   }
   const float cs = p.scale_log2;
-  // window of row a inside the 192-column band: c = 127 - a + b
-  const int win_q0 = (127 - a) >> 3, win_o = (127 - a) & 7;
+  // this thread's 32 values sit at band columns c = 127 - a + 32*half + bb
+  const int win_base = 127 - a + 32 * half;
+  const int win_q0 = win_base >> 3, win_o = win_base & 7;
 
   for (int st = 0; st < nsteps; ++st) {
     const int i0 = (qi0 + st) * FB_BM;
     const int i = i0 + a;
     const bool row_ok = i < p.L;
     const int64_t stat = (static_cast<int64_t>(b) * p.H + h) * p.L + i;
-    float lse2 = INFINITY, Di = 0.f;
+    float l_nat = -INFINITY, Di = 0.f;
     if (row_ok) {
-      const float l_nat = p.lse[stat];
-      lse2 = (l_nat == -INFINITY) ? INFINITY : l_nat * 1.4426950408889634f;
+      l_nat = p.lse[stat];
       Di = p.dsum[stat];
     }
     if (tid == 0) {
@@ -179,25 +199,22 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     }
     __syncwarp();
 
-    const int lim = i - j0;
-    uint32_t v0 = lim >= 31 ? 0xffffffffu : (lim < 0 ? 0u : ((2u << lim) - 1u));
-    uint32_t v1 = lim >= 63 ? 0xffffffffu : (lim < 32 ? 0u : ((2u << (lim - 32)) - 1u));
-    v0 &= ~kp0;
-    v1 &= ~kp1;
+    const int lim = i - j0 - 32 * half;  // this thread's columns bb <= lim are causal-visible
+    uint32_t vm = lim >= 31 ? 0xffffffffu : (lim < 0 ? 0u : ((2u << lim) - 1u));
+    vm &= ~kpm;
 
     mbar_wait(m1_done, st & 1);
     tc_fence_after();
+    const float lse2 = (!row_ok || l_nat == -INFINITY) ? INFINITY : l_nat * 1.4426950408889634f;
 
-    uint32_t pw[32], dw[36];  // bf16x2 words of P[a, :] and dS[a, :] (+ 4 zero words for the band shift)
-#pragma unroll
-    for (int ch = 0; ch < 2; ++ch) {
+    uint32_t pw[16], dw[20];  // bf16x2 words of P[a, 32h..] and dS[a, 32h..] (+ 4 zero words for the band shift)
+    {
       uint32_t sv[32], dpv[32], rv[64];
-      tmem_ld32(t_lane + FB_COL_S + 32 * ch, sv);
-      tmem_ld32(t_lane + FB_COL_DP + 32 * ch, dpv);
-      tmem_ld64(t_lane + FB_COL_R + 96 - 32 * warp + 32 * ch, rv);
+      tmem_ld32(t_lane + FB_COL_S + 32 * half, sv);
+      tmem_ld32(t_lane + FB_COL_DP + 32 * half, dpv);
+      tmem_ld64(t_lane + FB_COL_R + 96 - 32 * quarter + 32 * half, rv);
       tc_wait_ld();
       skew_select(rv, shift);
-      const uint32_t vm = ch == 0 ? v0 : v1;
 #pragma unroll
       for (int bb = 0; bb < 32; bb += 2) {
         float pr[2], dr[2];
@@ -211,8 +228,8 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         }
         __nv_bfloat162 ph2 = __floats2bfloat162_rn(pr[0], pr[1]);
         __nv_bfloat162 dh2 = __floats2bfloat162_rn(dr[0], dr[1]);
-        pw[16 * ch + bb / 2] = *reinterpret_cast<uint32_t*>(&ph2);
-        dw[16 * ch + bb / 2] = *reinterpret_cast<uint32_t*>(&dh2);
+        pw[bb / 2] = *reinterpret_cast<uint32_t*>(&ph2);
+        dw[bb / 2] = *reinterpret_cast<uint32_t*>(&dh2);
       }
     }
     // P and dS rows: UMMA SWIZZLE_128B rows of 128 B (chunk kc of row a at position kc ^ (a & 7))
@@ -220,28 +237,43 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       uint8_t* prow = sP + a * 128;
       uint8_t* drow = sdS + a * 128;
 #pragma unroll
-      for (int kc = 0; kc < 8; ++kc) {
-        const int pos = (kc ^ (a & 7)) << 4;
-        *reinterpret_cast<uint4*>(prow + pos) = make_uint4(pw[4 * kc], pw[4 * kc + 1], pw[4 * kc + 2], pw[4 * kc + 3]);
-        *reinterpret_cast<uint4*>(drow + pos) = make_uint4(dw[4 * kc], dw[4 * kc + 1], dw[4 * kc + 2], dw[4 * kc + 3]);
+      for (int n = 0; n < 4; ++n) {
+        const int pos = (((4 * half + n) ^ (a & 7))) << 4;
+        *reinterpret_cast<uint4*>(prow + pos) = make_uint4(pw[4 * n], pw[4 * n + 1], pw[4 * n + 2], pw[4 * n + 3]);
+        *reinterpret_cast<uint4*>(drow + pos) = make_uint4(dw[4 * n], dw[4 * n + 1], dw[4 * n + 2], dw[4 * n + 3]);
       }
     }
-    // dS row in band coordinates: shift right by win_o (0..7) elements inside a 72-element span
+    // dS in band coordinates: shift right by win_o (0..7) elements inside a 40-element span.  Chunk 4 of
+    // the lower half and chunk 0 of the upper half are the same 16 bytes: both sides write only their own
+    // elements there (2-byte stores), every other chunk is written whole.
     {
-      dw[32] = dw[33] = dw[34] = dw[35] = 0u;
+      dw[16] = dw[17] = dw[18] = dw[19] = 0u;
       const uint32_t on4 = win_o & 4, on2 = win_o & 2;
 #pragma unroll
-      for (int w = 35; w >= 0; --w) dw[w] = sel_b32(w >= 2 ? dw[w - 2] : 0u, dw[w], on4);
+      for (int w = 19; w >= 0; --w) dw[w] = sel_b32(w >= 2 ? dw[w - 2] : 0u, dw[w], on4);
 #pragma unroll
-      for (int w = 35; w >= 0; --w) dw[w] = sel_b32(w >= 1 ? dw[w - 1] : 0u, dw[w], on2);
+      for (int w = 19; w >= 0; --w) dw[w] = sel_b32(w >= 1 ? dw[w - 1] : 0u, dw[w], on2);
       const uint32_t hs = (win_o & 1) ? 16u : 0u;
 #pragma unroll
-      for (int w = 35; w >= 0; --w) dw[w] = __funnelshift_l(w >= 1 ? dw[w - 1] : 0u, dw[w], hs);
+      for (int w = 19; w >= 0; --w) dw[w] = __funnelshift_l(w >= 1 ? dw[w - 1] : 0u, dw[w], hs);
+      auto chunk_ptr = [&](int q) -> uint8_t* {
+        return sdSb + (q >> 3) * 16384 + a * 128 + (((q & 7) ^ (a & 7)) << 4);
+      };
+      const int shared_n = half == 0 ? 4 : 0;  // index (in this thread's span) of the chunk shared with the other half
 #pragma unroll
-      for (int n = 0; n < 9; ++n) {
-        const int q = win_q0 + n;  // 16-byte chunk index inside the 192-column band row (0..23)
-        uint8_t* dst = sdSb + (q >> 3) * 16384 + a * 128 + (((q & 7) ^ (a & 7)) << 4);
-        *reinterpret_cast<uint4*>(dst) = make_uint4(dw[4 * n], dw[4 * n + 1], dw[4 * n + 2], dw[4 * n + 3]);
+      for (int n = 0; n < 5; ++n) {
+        uint8_t* dst = chunk_ptr(win_q0 + n);
+        if (n != shared_n) {
+          *reinterpret_cast<uint4*>(dst) = make_uint4(dw[4 * n], dw[4 * n + 1], dw[4 * n + 2], dw[4 * n + 3]);
+        } else {
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+            const bool mine = half == 0 ? (e < win_o) : (e >= win_o);
+            const uint32_t word = dw[4 * n + e / 2];
+            const uint16_t val = static_cast<uint16_t>((e & 1) ? (word >> 16) : (word & 0xFFFFu));
+            if (mine) *reinterpret_cast<uint16_t*>(dst + 2 * e) = val;
+          }
+        }
       }
     }
     fence_proxy_async_smem();
@@ -283,86 +315,65 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     if (tid == 0 && st + 1 < nsteps) load_step(st + 1);  // Q / dO / E buffers are free again
     __syncwarp();
 
-    // dQ tile and dE tile: TMEM -> padded fp32 rows in shared memory -> TMA reduce-add
+    // dQ tile and dE tile: TMEM -> padded fp32 rows in shared memory -> one TMA reduce-add per 32 rows
     const int e0 = p.max_seq - FB_BM - (i0 - j0);
-    {
-      float* row = reinterpret_cast<float*>(stg0 + a * FB_STG_STRIDE);
-#pragma unroll
-      for (int c0 = 0; c0 < DH; c0 += 16) {
-        uint32_t v[16];
-        tmem_ld16(t_lane + FB_COL_DQ + c0, v);
-        tc_wait_ld();
-#pragma unroll
-        for (int c = 0; c < 16; c += 4)
-          *reinterpret_cast<uint4*>(row + c0 + c) = make_uint4(v[c], v[c + 1], v[c + 2], v[c + 3]);
-      }
-      float* row1 = reinterpret_cast<float*>(stg1 + a * FB_STG_STRIDE);
-#pragma unroll
-      for (int c0 = 0; c0 < DH; c0 += 16) {
-        uint32_t v[16];
-        tmem_ld16(t_lane + FB_COL_DE_LO + c0, v);
-        tc_wait_ld();
-#pragma unroll
-        for (int c = 0; c < 16; c += 4)
-          *reinterpret_cast<uint4*>(row1 + c0 + c) = make_uint4(v[c], v[c + 1], v[c + 2], v[c + 3]);
-      }
-      float* row2 = reinterpret_cast<float*>(sP + a * FB_STG_STRIDE);  // P / dS are free after MMA 2
-      if (warp < 2) {
-#pragma unroll
-        for (int c0 = 0; c0 < DH; c0 += 16) {
-          uint32_t v[16];
-          tmem_ld16(t_lane + FB_COL_DE_HI + c0, v);
-          tc_wait_ld();
-#pragma unroll
-          for (int c = 0; c < 16; c += 4)
-            *reinterpret_cast<uint4*>(row2 + c0 + c) = make_uint4(v[c], v[c + 1], v[c + 2], v[c + 3]);
+    stage_row<HC>(t_lane + FB_COL_DQ + half * HC, reinterpret_cast<float*>(stg0 + a * STG) + half * HC);
+    stage_row<HC>(t_lane + FB_COL_DE_LO + half * HC, reinterpret_cast<float*>(stg1 + a * STG) + half * HC);
+    if (quarter < 2)
+      stage_row<HC>(t_lane + FB_COL_DE_HI + half * HC, reinterpret_cast<float*>(stg2 + a * STG) + half * HC);
+    fence_proxy_async_smem();
+    tc_fence_before();
+    __syncthreads();  // staging complete (both column halves of every row)
+    if (lane == 0) {
+      const int r0 = 32 * quarter;
+      if (half == 0) {
+        const int n = min(32, p.L - (i0 + r0));
+        if (n > 0)
+          bulk_reduce_add_f32(p.dq_ws + ((static_cast<int64_t>(b) * p.H + h) * p.L + i0 + r0) * (DH + 4),
+                              stg0 + r0 * STG, n * STG);
+      } else {
+        const int n = min(32, p.max_seq - (e0 + r0));
+        if (n > 0) bulk_reduce_add_f32(p.dE_ws + static_cast<int64_t>(e0 + r0) * (DH + 4), stg1 + r0 * STG, n * STG);
+        if (quarter < 2) {
+          const int n2 = min(32, p.max_seq - (e0 + 128 + r0));
+          if (n2 > 0)
+            bulk_reduce_add_f32(p.dE_ws + static_cast<int64_t>(e0 + 128 + r0) * (DH + 4), stg2 + r0 * STG, n2 * STG);
         }
       }
-      fence_proxy_async_smem();
-      if (row_ok)
-        bulk_reduce_add_f32(p.dq_acc + static_cast<int64_t>(b) * p.dq_sb + static_cast<int64_t>(i) * p.dq_si + h * DH,
-                            row, DH * 4);
-      if (e0 + a < p.max_seq) bulk_reduce_add_f32(p.dE + static_cast<int64_t>(e0 + a) * DH, row1, DH * 4);
-      if (warp < 2 && e0 + 128 + a < p.max_seq)
-        bulk_reduce_add_f32(p.dE + static_cast<int64_t>(e0 + 128 + a) * DH, row2, DH * 4);
       bulk_commit();
       bulk_wait_read_all();  // staging rows (and the P/dS area) may be overwritten afterwards
     }
-    tc_fence_before();
     __syncthreads();  // all TMEM tiles of this step have been read; shared staging is reusable
   }
 
-  // dK / dV: rows 0..63 of the accumulators (lanes 0..63 = warps 0, 1)
+  // dK / dV: rows 0..63 of the accumulators (TMEM lanes 0..63: quarters 0 and 1), columns split by half
   tc_fence_after();
-  if (warp < 2) {
+  if (quarter < 2) {
     const int j = j0 + a;
     const bool key_ok = j < p.L;
-    bf16* dkrow = p.dk + static_cast<int64_t>(b) * p.k_sb + static_cast<int64_t>(j) * p.k_sj + h * p.k_sh;
-    bf16* dvrow = p.dv + static_cast<int64_t>(b) * p.v_sb + static_cast<int64_t>(j) * p.v_sj + h * p.v_sh;
+    bf16* dkrow = p.dk + static_cast<int64_t>(b) * p.k_sb + static_cast<int64_t>(j) * p.k_sj + h * p.k_sh + half * HC;
+    bf16* dvrow = p.dv + static_cast<int64_t>(b) * p.v_sb + static_cast<int64_t>(j) * p.v_sj + h * p.v_sh + half * HC;
 #pragma unroll
-    for (int c0 = 0; c0 < DH; c0 += 16) {
-      uint32_t vk[16], vv[16];
-      tmem_ld16(t_lane + FB_COL_DK + c0, vk);  // .sync.aligned: every lane of the warp takes part
-      tmem_ld16(t_lane + FB_COL_DV + c0, vv);
+    for (int c0 = 0; c0 < HC; c0 += 8) {
+      uint32_t vk[8], vv[8];
+      tmem_ld8(t_lane + FB_COL_DK + half * HC + c0, vk);
+      tmem_ld8(t_lane + FB_COL_DV + half * HC + c0, vv);
       tc_wait_ld();
       if (key_ok) {
+        uint4 uk, uv;
+        __nv_bfloat162* hk = reinterpret_cast<__nv_bfloat162*>(&uk);
+        __nv_bfloat162* hv = reinterpret_cast<__nv_bfloat162*>(&uv);
 #pragma unroll
-        for (int c = 0; c < 16; c += 8) {
-          uint4 uk, uv;
-          __nv_bfloat162* hk = reinterpret_cast<__nv_bfloat162*>(&uk);
-          __nv_bfloat162* hv = reinterpret_cast<__nv_bfloat162*>(&uv);
-#pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            hk[e] = __floats2bfloat162_rn(__uint_as_float(vk[c + 2 * e]), __uint_as_float(vk[c + 2 * e + 1]));
-            hv[e] = __floats2bfloat162_rn(__uint_as_float(vv[c + 2 * e]), __uint_as_float(vv[c + 2 * e + 1]));
-          }
-          *reinterpret_cast<uint4*>(dkrow + c0 + c) = uk;
-          *reinterpret_cast<uint4*>(dvrow + c0 + c) = uv;
+        for (int e = 0; e < 4; ++e) {
+          hk[e] = __floats2bfloat162_rn(__uint_as_float(vk[2 * e]), __uint_as_float(vk[2 * e + 1]));
+          hv[e] = __floats2bfloat162_rn(__uint_as_float(vv[2 * e]), __uint_as_float(vv[2 * e + 1]));
         }
+        *reinterpret_cast<uint4*>(dkrow + c0) = uk;
+        *reinterpret_cast<uint4*>(dvrow + c0) = uv;
       }
     }
   }
-  bulk_wait_all();
+  if (lane == 0) bulk_wait_all();
   tc_fence_before();
   __syncthreads();
   if (warp == 0) {
@@ -400,22 +411,37 @@ __global__ void attn_bwd_prep_kernel(const bf16* __restrict__ out, const bf16* _
   dsum[(static_cast<int64_t>(b) * H + h) * L + i] = acc;
 }
 
-// dq (bf16, strided) = dq_acc (fp32 [B, L, H*dh])
-__global__ void attn_bwd_dq_convert_kernel(const float* __restrict__ acc, bf16* __restrict__ dq, int64_t q_sb,
-                                           int64_t q_si, int L, int d, int64_t total4) {
-  for (int64_t i4 = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i4 < total4;
-       i4 += static_cast<int64_t>(gridDim.x) * blockDim.x) {
-    const int64_t e = i4 * 4;
-    const int c = static_cast<int>(e % d);
-    const int64_t row = e / d;
-    const int i = static_cast<int>(row % L);
-    const int64_t b = row / L;
-    const float4 v = *reinterpret_cast<const float4*>(acc + e);
-    __nv_bfloat162 lo = __floats2bfloat162_rn(v.x, v.y), hi = __floats2bfloat162_rn(v.z, v.w);
-    uint2 u;
-    u.x = *reinterpret_cast<uint32_t*>(&lo);
-    u.y = *reinterpret_cast<uint32_t*>(&hi);
-    *reinterpret_cast<uint2*>(dq + b * q_sb + i * q_si + c) = u;
+// dq (bf16, strided) = dq_ws (fp32 [B, H, L, dh + 4]);  dE[e, :] += dE_ws[e, :] (rows padded likewise)
+__global__ void attn_bwd_finish_kernel(const float* __restrict__ dq_ws, bf16* __restrict__ dq, int64_t q_sb,
+                                       int64_t q_si, int64_t q_sh, int B, int H, int L, int dh,
+                                       const float* __restrict__ dE_ws, float* __restrict__ dE, int max_seq) {
+  const int q4 = dh / 4;
+  const int64_t n_dq = static_cast<int64_t>(B) * H * L * q4;
+  const int64_t n_de = static_cast<int64_t>(max_seq) * q4;
+  for (int64_t t = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; t < n_dq + n_de;
+       t += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    if (t < n_dq) {
+      const int c = static_cast<int>(t % q4) * 4;
+      const int64_t row = t / q4;  // (b*H + h)*L + i
+      const int i = static_cast<int>(row % L);
+      const int64_t bh = row / L;
+      const int h = static_cast<int>(bh % H);
+      const int64_t b = bh / H;
+      const float4 v = *reinterpret_cast<const float4*>(dq_ws + row * (dh + 4) + c);
+      __nv_bfloat162 lo = __floats2bfloat162_rn(v.x, v.y), hi = __floats2bfloat162_rn(v.z, v.w);
+      uint2 u;
+      u.x = *reinterpret_cast<uint32_t*>(&lo);
+      u.y = *reinterpret_cast<uint32_t*>(&hi);
+      *reinterpret_cast<uint2*>(dq + b * q_sb + i * q_si + h * q_sh + c) = u;
+    } else {
+      const int64_t u = t - n_dq;
+      const int c = static_cast<int>(u % q4) * 4;
+      const int64_t e = u / q4;
+      const float4 v = *reinterpret_cast<const float4*>(dE_ws + e * (dh + 4) + c);
+      float4 o = *reinterpret_cast<float4*>(dE + e * dh + c);
+      o.x += v.x; o.y += v.y; o.z += v.z; o.w += v.w;
+      *reinterpret_cast<float4*>(dE + e * dh + c) = o;
+    }
   }
 }
 
@@ -440,9 +466,10 @@ int launch_attn_bwd_tc(const me_attn_bwd_args* ba) {
   ME_CHECK(a->dh == 32 || a->dh == 48 || a->dh == 64, "me_attention_backward: ME_ATTN_TENSOR supports head dim 32/48/64 (got %d)", a->dh);
   ME_CHECK(a->q_pos0 == 0 && a->Lq == a->Lk && a->pos_dev == nullptr, "me_attention_backward: self-attention only");
   ME_CHECK(a->lse && ba->dsum && ba->dE && ba->dq_acc, "me_attention_backward: lse/dsum/dE/dq_acc required");
+  ME_CHECK((reinterpret_cast<uintptr_t>(ba->dq_acc) & 15) == 0, "me_attention_backward: dq_acc must be 16-byte aligned");
   ME_CHECK(a->q_sh == a->dh && a->k_sh == a->dh && a->v_sh == a->dh,
            "me_attention_backward: ME_ATTN_TENSOR expects heads packed along the feature axis (stride dh)");
-  const int B = a->B, H = a->H, L = a->Lq, dh = a->dh, d = H * dh;
+  const int B = a->B, H = a->H, L = a->Lq, dh = a->dh;
   cudaStream_t st = static_cast<cudaStream_t>(a->stream);
   CUtensorMap tq, tk, tv, tdo, te;
   if (qkv_map(&tq, a->q, dh, H, L, B, a->q_sh, a->q_si, a->q_sb, FB_BM)) return 1;
@@ -465,15 +492,16 @@ int launch_attn_bwd_tc(const me_attn_bwd_args* ba) {
     else if (dh == 48) attn_bwd_prep_kernel<48><<<blocks, 128, 0, st>>>(o, g, a->o_sb, a->o_si, B, H, L, ba->dsum);
     else attn_bwd_prep_kernel<32><<<blocks, 128, 0, st>>>(o, g, a->o_sb, a->o_si, B, H, L, ba->dsum);
     ME_LAUNCH_CHECK();
-    ME_CUDA(cudaMemsetAsync(ba->dq_acc, 0, static_cast<size_t>(B) * L * d * sizeof(float), st));
+    ME_CUDA(cudaMemsetAsync(ba->dq_acc, 0, sizeof(float) * me_attention_backward_workspace_floats(B, H, L, dh, a->max_seq), st));
   }
   FbParams p;
   p.B = B; p.H = H; p.L = L; p.max_seq = a->max_seq;
   p.k_sb = a->k_sb; p.k_sh = a->k_sh; p.k_sj = a->k_sj;
   p.v_sb = a->v_sb; p.v_sh = a->v_sh; p.v_sj = a->v_sj;
   p.keypad_ld = a->keypad_ld; p.keypad = a->keypad;
-  p.dq_sb = static_cast<int64_t>(L) * d; p.dq_si = d;
-  p.lse = a->lse; p.dsum = ba->dsum; p.dq_acc = ba->dq_acc; p.dE = ba->dE;
+  p.lse = a->lse; p.dsum = ba->dsum;
+  p.dq_ws = ba->dq_acc;
+  p.dE_ws = ba->dq_acc + static_cast<int64_t>(B) * H * L * (dh + 4);
   p.dk = static_cast<bf16*>(ba->dk); p.dv = static_cast<bf16*>(ba->dv);
   p.scale = 1.f / sqrtf(static_cast<float>(dh));
   p.scale_log2 = 1.4426950408889634f * p.scale;
@@ -484,14 +512,18 @@ int launch_attn_bwd_tc(const me_attn_bwd_args* ba) {
   else rc = launch_bwd<32>(tq, tk, tv, tdo, te, p, grid, st);
   if (rc) return rc;
   {
-    const int64_t total4 = static_cast<int64_t>(B) * L * d / 4;
-    const int64_t want = (total4 + 255) / 256;
+    const int64_t total = (static_cast<int64_t>(B) * H * L + a->max_seq) * (dh / 4);
+    const int64_t want = (total + 255) / 256;
     const int blocks = static_cast<int>(want < 148 * 16 ? want : 148 * 16);
-    attn_bwd_dq_convert_kernel<<<blocks, 256, 0, st>>>(ba->dq_acc, static_cast<bf16*>(ba->dq), a->q_sb, a->q_si, L, d,
-                                                      total4);
+    attn_bwd_finish_kernel<<<blocks, 256, 0, st>>>(p.dq_ws, static_cast<bf16*>(ba->dq), a->q_sb, a->q_si, a->q_sh, B, H,
+                                                   L, dh, p.dE_ws, ba->dE, a->max_seq);
     ME_LAUNCH_CHECK();
   }
   return 0;
 }
 
 }  // namespace me
+
+extern "C" int64_t me_attention_backward_workspace_floats(int B, int H, int L, int dh, int max_seq) {
+  return (static_cast<int64_t>(B) * H * L + max_seq) * (dh + 4);
+}

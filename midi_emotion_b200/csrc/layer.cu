@@ -126,6 +126,7 @@ extern "C" int me_layer_backward(const me_layer_bwd_args* b) {
                b->dW1 && b->db1 && b->dW2 && b->db2 && b->dln2_w && b->dln2_b,
            "me_layer_backward: NULL gradient pointer");
   ME_CHECK(b->g_a && b->g_b && b->g_T && b->g_h && b->g_qkv && b->g_o && b->dsum, "me_layer_backward: NULL scratch");
+  ME_CHECK(a->attn_impl != ME_ATTN_TENSOR || b->attn_ws, "me_layer_backward: attn_ws required for ME_ATTN_TENSOR");
   cudaStream_t st = static_cast<cudaStream_t>(a->stream);
   const int d = a->d, di = a->d_inner, M = a->B * a->Ls, dt = a->dtype, H = a->H, dh = d / H;
   const float p = a->training ? a->dropout_p : 0.f;
@@ -178,7 +179,7 @@ extern "C" int me_layer_backward(const me_layer_bwd_args* b) {
   t.dv = offs(b->g_qkv, dt, 2 * d);
   t.dE = b->dE;
   t.dsum = b->dsum;
-  t.dq_acc = b->g_b;  // free at this point: LayerNorm-1 backward has consumed it
+  t.dq_acc = b->attn_ws;
   if (me_attention_backward(&t)) return 1;
 
   if (launch_colsum(b->g_qkv, dt, M, 3 * d, 3 * d, b->dbqkv, st)) return 1;

@@ -358,7 +358,7 @@ def _run_attention_backward(impl, a, qkv, out, lse, dout, B, H, L, dh):
     g_qkv = torch.full_like(qkv, float("nan"))
     dE = torch.zeros(2048, dh, device="cuda")
     dsum = torch.empty(B, H, L, device="cuda")
-    dq_acc = torch.empty(B, L, d, device="cuda")
+    dq_acc = torch.empty(_lib.load().me_attention_backward_workspace_floats(B, H, L, dh, 2048), device="cuda")
     ba = _lib.AttnBwdArgs()
     ba.f = a
     ba.f.impl = impl
