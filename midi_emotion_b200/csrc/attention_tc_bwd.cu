@@ -23,7 +23,9 @@ namespace me {
 constexpr int FB_BM = 128;            // query rows per step
 constexpr int FB_BN = 64;             // keys per CTA
 constexpr int FB_EROWS = 192;
-constexpr int FB_THREADS = 256;       // 8 warps: warp w and w+4 share TMEM lanes 32*(w&3).. and split the key columns
+constexpr int FB_COMPUTE_THREADS = 256;  // 8 warps: warp w and w+4 share TMEM lanes 32*(w&3).. and split the key columns
+constexpr int FB_CONTROL_WARP = 8;       // one more warp: TMA producer + MMA issuer, TMEM alloc
+constexpr int FB_THREADS = FB_COMPUTE_THREADS + 32;
 constexpr int FB_STG_MAX = 272;       // staging row pitch for dh = 64: (dh + 4) floats
 constexpr int FB_OFF_K = 0;
 constexpr int FB_OFF_V = FB_OFF_K + 8192;
@@ -96,290 +98,308 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   uint64_t* bars = reinterpret_cast<uint64_t*>(fb_smem + FB_OFF_BAR);
   uint64_t* kv_full = bars + 0;
   uint64_t* ld_full = bars + 1;
-  uint64_t* m1_done = bars + 2;
-  uint64_t* m2_done = bars + 3;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 4);
+  uint64_t* m1_done = bars + 2;   // S, dP, R ready
+  uint64_t* a_done = bars + 3;    // P, dS, dSb written (256 arrivals)
+  uint64_t* m2q_done = bars + 4;  // dQ tile ready
+  uint64_t* m2b_done = bars + 5;  // dV, dK accumulated: P, dS, Q, dO, E are free
+  uint64_t* m2e_done = bars + 6;  // dE tile ready
+  uint64_t* b_done = bars + 7;    // TMEM tiles of the step read out (256 arrivals)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int half = warp >> 2, quarter = warp & 3;
   const int kt = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
   const int j0 = kt * FB_BN;
   const int nq = (p.L + FB_BM - 1) / FB_BM;
   const int qi0 = j0 / FB_BM;
   const int nsteps = nq - qi0;
 
-  auto load_step = [&](int st) {
-    const int i0 = (qi0 + st) * FB_BM;
-    mbar_arrive_expect_tx(ld_full, 16384 + 16384 + 24576);
-    tma_load_4d(&tmQ, ld_full, sQ, 0, h, i0, b);
-    tma_load_4d(&tmdO, ld_full, sdO, 0, h, i0, b);
-    tma_load_2d(&tmE, ld_full, sE, 0, p.max_seq - FB_BM - (i0 - j0));
-  };
-
   if (tid == 0) {
     if ((smem_u32(fb_smem) & 1023u) != 0) __trap();
-    tma_prefetch_desc(&tmQ);
-    tma_prefetch_desc(&tmK);
-    tma_prefetch_desc(&tmV);
-    tma_prefetch_desc(&tmdO);
-    tma_prefetch_desc(&tmE);
     mbar_init(kv_full, 1);
     mbar_init(ld_full, 1);
     mbar_init(m1_done, 1);
-    mbar_init(m2_done, 1);
+    mbar_init(a_done, FB_COMPUTE_THREADS);
+    mbar_init(m2q_done, 1);
+    mbar_init(m2b_done, 1);
+    mbar_init(m2e_done, 1);
+    mbar_init(b_done, FB_COMPUTE_THREADS);
     fence_mbar_init();
-    mbar_arrive_expect_tx(kv_full, 16384);
-    tma_load_4d(&tmK, kv_full, sK, 0, h, j0, b);
-    tma_load_4d(&tmV, kv_full, sV, 0, h, j0, b);
-    load_step(0);
   }
   // dSb starts as zeros; every step rewrites only the chunks around each row's window
   {
     uint4* z = reinterpret_cast<uint4*>(sdSb);
     for (int c = tid; c < 49152 / 16; c += FB_THREADS) z[c] = make_uint4(0, 0, 0, 0);
   }
-  if (warp == 0) {
-    __syncwarp();
-    tmem_alloc(tmem_slot, FB_TMEM_COLS);
-  }
+  if (warp == FB_CONTROL_WARP) tmem_alloc(tmem_slot, FB_TMEM_COLS);
   fence_proxy_async_smem();
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  constexpr uint32_t idesc_s = make_idesc_bf16(128, FB_BN, 0, 0);     // S, dP : K-major x K-major
-  constexpr uint32_t idesc_r = make_idesc_bf16(128, FB_EROWS, 0, 0);  // R
-  constexpr uint32_t idesc_tt = make_idesc_bf16(128, DH, 1, 1);       // dV, dK, dE : A^T (MN-major) x B (MN-major)
-  constexpr uint32_t idesc_nt = make_idesc_bf16(128, DH, 0, 1);       // dQ : A (K-major) x B (MN-major)
-  const uint32_t k_addr = smem_u32(sK), v_addr = smem_u32(sV), q_addr = smem_u32(sQ), do_addr = smem_u32(sdO);
-  const uint32_t e_addr = smem_u32(sE), p_addr = smem_u32(sP), ds_addr = smem_u32(sdS), dsb_addr = smem_u32(sdSb);
-
-  const int a = quarter * 32 + lane;   // query row inside the tile == TMEM lane
-  const int shift = 31 - lane;
-  const uint32_t t_lane = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16);
-  const uint8_t* kp = p.keypad ? p.keypad + static_cast<int64_t>(b) * p.keypad_ld : nullptr;
-  uint32_t kpm = 0;  // key-pad bits of this thread's 32 keys
-  if (kp) {
-    const int j = j0 + 32 * half + lane;
-    kpm = __ballot_sync(0xffffffffu, j < p.L && kp[j] != 0);
-  }
-  const float cs = p.scale_log2;
-  // this thread's 32 values sit at band columns c = 127 - a + 32*half + bb
-  const int win_base = 127 - a + 32 * half;
-  const int win_q0 = win_base >> 3, win_o = win_base & 7;
-
-  for (int st = 0; st < nsteps; ++st) {
-    const int i0 = (qi0 + st) * FB_BM;
-    const int i = i0 + a;
-    const bool row_ok = i < p.L;
-    const int64_t stat = (static_cast<int64_t>(b) * p.H + h) * p.L + i;
-    float l_nat = -INFINITY, Di = 0.f;
-    if (row_ok) {
-      l_nat = p.lse[stat];
-      Di = p.dsum[stat];
-    }
-    if (tid == 0) {
-      if (st == 0) mbar_wait(kv_full, 0);
-      mbar_wait(ld_full, st & 1);
-      tc_fence_after();
-#pragma unroll
-      for (int k = 0; k < DH / 16; ++k)
-        umma_bf16(tmem_base + FB_COL_S, make_smem_desc_sw128(q_addr + k * 32, 16, 1024),
-                  make_smem_desc_sw128(k_addr + k * 32, 16, 1024), idesc_s, k > 0);
-#pragma unroll
-      for (int k = 0; k < DH / 16; ++k)
-        umma_bf16(tmem_base + FB_COL_DP, make_smem_desc_sw128(do_addr + k * 32, 16, 1024),
-                  make_smem_desc_sw128(v_addr + k * 32, 16, 1024), idesc_s, k > 0);
-#pragma unroll
-      for (int k = 0; k < DH / 16; ++k)
-        umma_bf16(tmem_base + FB_COL_R, make_smem_desc_sw128(q_addr + k * 32, 16, 1024),
-                  make_smem_desc_sw128(e_addr + k * 32, 16, 1024), idesc_r, k > 0);
-      umma_commit(m1_done);
-    }
-    __syncwarp();
-
-    const int lim = i - j0 - 32 * half;  // this thread's columns bb <= lim are causal-visible
-    uint32_t vm = lim >= 31 ? 0xffffffffu : (lim < 0 ? 0u : ((2u << lim) - 1u));
-    vm &= ~kpm;
-
-    mbar_wait(m1_done, st & 1);
-    tc_fence_after();
-    const float lse2 = (!row_ok || l_nat == -INFINITY) ? INFINITY : l_nat * 1.4426950408889634f;
-
-    uint32_t pw[16], dw[20];  // bf16x2 words of P[a, 32h..] and dS[a, 32h..] (+ 4 zero words for the band shift)
-    {
-      uint32_t sv[32], dpv[32], rv[64];
-      tmem_ld32(t_lane + FB_COL_S + 32 * half, sv);
-      tmem_ld32(t_lane + FB_COL_DP + 32 * half, dpv);
-      tmem_ld64(t_lane + FB_COL_R + 96 - 32 * quarter + 32 * half, rv);
-      tc_wait_ld();
-      skew_select(rv, shift);
-#pragma unroll
-      for (int bb = 0; bb < 32; bb += 2) {
-        float pr[2], dr[2];
-#pragma unroll
-        for (int e = 0; e < 2; ++e) {
-          const float x = __uint_as_float(sv[bb + e]) + __uint_as_float(rv[bb + e]);
-          float pe = fast_exp2(fmaf(x, cs, -lse2));
-          if (!((vm >> (bb + e)) & 1u)) pe = 0.f;
-          pr[e] = pe;
-          dr[e] = pe * (__uint_as_float(dpv[bb + e]) - Di) * p.scale;
-        }
-        __nv_bfloat162 ph2 = __floats2bfloat162_rn(pr[0], pr[1]);
-        __nv_bfloat162 dh2 = __floats2bfloat162_rn(dr[0], dr[1]);
-        pw[bb / 2] = *reinterpret_cast<uint32_t*>(&ph2);
-        dw[bb / 2] = *reinterpret_cast<uint32_t*>(&dh2);
-      }
-    }
-    // P and dS rows: UMMA SWIZZLE_128B rows of 128 B (chunk kc of row a at position kc ^ (a & 7))
-    {
-      uint8_t* prow = sP + a * 128;
-      uint8_t* drow = sdS + a * 128;
-#pragma unroll
-      for (int n = 0; n < 4; ++n) {
-        const int pos = (((4 * half + n) ^ (a & 7))) << 4;
-        *reinterpret_cast<uint4*>(prow + pos) = make_uint4(pw[4 * n], pw[4 * n + 1], pw[4 * n + 2], pw[4 * n + 3]);
-        *reinterpret_cast<uint4*>(drow + pos) = make_uint4(dw[4 * n], dw[4 * n + 1], dw[4 * n + 2], dw[4 * n + 3]);
-      }
-    }
-    // dS in band coordinates: shift right by win_o (0..7) elements inside a 40-element span.  Chunk 4 of
-    // the lower half and chunk 0 of the upper half are the same 16 bytes: both sides write only their own
-    // elements there (2-byte stores), every other chunk is written whole.
-    {
-      dw[16] = dw[17] = dw[18] = dw[19] = 0u;
-      const uint32_t on4 = win_o & 4, on2 = win_o & 2;
-#pragma unroll
-      for (int w = 19; w >= 0; --w) dw[w] = sel_b32(w >= 2 ? dw[w - 2] : 0u, dw[w], on4);
-#pragma unroll
-      for (int w = 19; w >= 0; --w) dw[w] = sel_b32(w >= 1 ? dw[w - 1] : 0u, dw[w], on2);
-      const uint32_t hs = (win_o & 1) ? 16u : 0u;
-#pragma unroll
-      for (int w = 19; w >= 0; --w) dw[w] = __funnelshift_l(w >= 1 ? dw[w - 1] : 0u, dw[w], hs);
-      auto chunk_ptr = [&](int q) -> uint8_t* {
-        return sdSb + (q >> 3) * 16384 + a * 128 + (((q & 7) ^ (a & 7)) << 4);
+  if (warp == FB_CONTROL_WARP) {
+    // ======================= TMA producer + MMA issuer (one thread) =======================
+    if (lane == 0) {
+      auto load_step = [&](int st) {
+        const int i0 = (qi0 + st) * FB_BM;
+        mbar_arrive_expect_tx(ld_full, 16384 + 16384 + 24576);
+        tma_load_4d(&tmQ, ld_full, sQ, 0, h, i0, b);
+        tma_load_4d(&tmdO, ld_full, sdO, 0, h, i0, b);
+        tma_load_2d(&tmE, ld_full, sE, 0, p.max_seq - FB_BM - (i0 - j0));
       };
-      const int shared_n = half == 0 ? 4 : 0;  // index (in this thread's span) of the chunk shared with the other half
+      tma_prefetch_desc(&tmQ);
+      tma_prefetch_desc(&tmK);
+      tma_prefetch_desc(&tmV);
+      tma_prefetch_desc(&tmdO);
+      tma_prefetch_desc(&tmE);
+      mbar_arrive_expect_tx(kv_full, 16384);
+      tma_load_4d(&tmK, kv_full, sK, 0, h, j0, b);
+      tma_load_4d(&tmV, kv_full, sV, 0, h, j0, b);
+      load_step(0);
+
+      constexpr uint32_t idesc_s = make_idesc_bf16(128, FB_BN, 0, 0);     // S, dP : K-major x K-major
+      constexpr uint32_t idesc_r = make_idesc_bf16(128, FB_EROWS, 0, 0);  // R
+      constexpr uint32_t idesc_tt = make_idesc_bf16(128, DH, 1, 1);       // dV, dK, dE : A^T (MN-major) x B (MN-major)
+      constexpr uint32_t idesc_nt = make_idesc_bf16(128, DH, 0, 1);       // dQ : A (K-major) x B (MN-major)
+      const uint32_t k_addr = smem_u32(sK), v_addr = smem_u32(sV), q_addr = smem_u32(sQ), do_addr = smem_u32(sdO);
+      const uint32_t e_addr = smem_u32(sE), p_addr = smem_u32(sP), ds_addr = smem_u32(sdS), dsb_addr = smem_u32(sdSb);
+      mbar_wait(kv_full, 0);
+      for (int st = 0; st < nsteps; ++st) {
+        const uint32_t ph = st & 1;
+        mbar_wait(ld_full, ph);
+        if (st > 0) mbar_wait(b_done, (st - 1) & 1);  // S / dP / R (and the dE alias) may be overwritten
+        tc_fence_after();
 #pragma unroll
-      for (int n = 0; n < 5; ++n) {
-        uint8_t* dst = chunk_ptr(win_q0 + n);
-        if (n != shared_n) {
-          *reinterpret_cast<uint4*>(dst) = make_uint4(dw[4 * n], dw[4 * n + 1], dw[4 * n + 2], dw[4 * n + 3]);
-        } else {
+        for (int k = 0; k < DH / 16; ++k)
+          umma_bf16(tmem_base + FB_COL_S, make_smem_desc_sw128(q_addr + k * 32, 16, 1024),
+                    make_smem_desc_sw128(k_addr + k * 32, 16, 1024), idesc_s, k > 0);
 #pragma unroll
-          for (int e = 0; e < 8; ++e) {
-            const bool mine = half == 0 ? (e < win_o) : (e >= win_o);
-            const uint32_t word = dw[4 * n + e / 2];
-            const uint16_t val = static_cast<uint16_t>((e & 1) ? (word >> 16) : (word & 0xFFFFu));
-            if (mine) *reinterpret_cast<uint16_t*>(dst + 2 * e) = val;
+        for (int k = 0; k < DH / 16; ++k)
+          umma_bf16(tmem_base + FB_COL_DP, make_smem_desc_sw128(do_addr + k * 32, 16, 1024),
+                    make_smem_desc_sw128(v_addr + k * 32, 16, 1024), idesc_s, k > 0);
+#pragma unroll
+        for (int k = 0; k < DH / 16; ++k)
+          umma_bf16(tmem_base + FB_COL_R, make_smem_desc_sw128(q_addr + k * 32, 16, 1024),
+                    make_smem_desc_sw128(e_addr + k * 32, 16, 1024), idesc_r, k > 0);
+        umma_commit(m1_done);
+
+        mbar_wait(a_done, ph);
+        tc_fence_after();
+#pragma unroll
+        for (int k = 0; k < 4; ++k)  // dQ_tile = dS K
+          umma_bf16(tmem_base + FB_COL_DQ, make_smem_desc_sw128(ds_addr + k * 32, 16, 1024),
+                    make_smem_desc_sw128(k_addr + k * 2048, 8192, 1024), idesc_nt, k > 0);
+#pragma unroll
+        for (int k = 0; k < 12; ++k)  // dQ_tile += dSb Eband
+          umma_bf16(tmem_base + FB_COL_DQ,
+                    make_smem_desc_sw128(dsb_addr + (k >> 2) * 16384 + (k & 3) * 32, 16, 1024),
+                    make_smem_desc_sw128(e_addr + k * 2048, 8192, 1024), idesc_nt, 1u);
+        umma_commit(m2q_done);
+        const uint32_t acc0 = st > 0 ? 1u : 0u;
+#pragma unroll
+        for (int k = 0; k < 8; ++k)  // dV += P^T dO
+          umma_bf16(tmem_base + FB_COL_DV, make_smem_desc_sw128(p_addr + k * 2048, 16384, 1024),
+                    make_smem_desc_sw128(do_addr + k * 2048, 8192, 1024), idesc_tt, (k > 0) ? 1u : acc0);
+#pragma unroll
+        for (int k = 0; k < 8; ++k)  // dK += dS^T Q
+          umma_bf16(tmem_base + FB_COL_DK, make_smem_desc_sw128(ds_addr + k * 2048, 16384, 1024),
+                    make_smem_desc_sw128(q_addr + k * 2048, 8192, 1024), idesc_tt, (k > 0) ? 1u : acc0);
+        umma_commit(m2b_done);
+#pragma unroll
+        for (int k = 0; k < 8; ++k)  // dE_tile[0:128] = dSb[:, 0:128]^T Q
+          umma_bf16(tmem_base + FB_COL_DE_LO, make_smem_desc_sw128(dsb_addr + k * 2048, 16384, 1024),
+                    make_smem_desc_sw128(q_addr + k * 2048, 8192, 1024), idesc_tt, k > 0);
+#pragma unroll
+        for (int k = 0; k < 8; ++k)  // dE_tile[128:192] = dSb[:, 128:192]^T Q (lanes 64..127 unused)
+          umma_bf16(tmem_base + FB_COL_DE_HI, make_smem_desc_sw128(dsb_addr + 32768 + k * 2048, 16384, 1024),
+                    make_smem_desc_sw128(q_addr + k * 2048, 8192, 1024), idesc_tt, k > 0);
+        umma_commit(m2e_done);
+        if (st + 1 < nsteps) {
+          mbar_wait(m2e_done, ph);  // every MMA of the step has retired: Q / dO / E may be reloaded
+          load_step(st + 1);
+        }
+      }
+    }
+  } else {
+    // ================================ compute warps ================================
+    const int half = warp >> 2, quarter = warp & 3;
+    const int a = quarter * 32 + lane;   // query row inside the tile == TMEM lane
+    const int shift = 31 - lane;
+    const uint32_t t_lane = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16);
+    const uint8_t* kp = p.keypad ? p.keypad + static_cast<int64_t>(b) * p.keypad_ld : nullptr;
+    uint32_t kpm = 0;  // key-pad bits of this thread's 32 keys
+    if (kp) {
+      const int j = j0 + 32 * half + lane;
+      kpm = __ballot_sync(0xffffffffu, j < p.L && kp[j] != 0);
+    }
+    const float cs = p.scale_log2;
+    // this thread's 32 values sit at band columns c = 127 - a + 32*half + bb
+    const int win_base = 127 - a + 32 * half;
+    const int win_q0 = win_base >> 3, win_o = win_base & 7;
+
+    for (int st = 0; st < nsteps; ++st) {
+      const uint32_t ph = st & 1;
+      const int i0 = (qi0 + st) * FB_BM;
+      const int i = i0 + a;
+      const bool row_ok = i < p.L;
+      const int64_t stat = (static_cast<int64_t>(b) * p.H + h) * p.L + i;
+      float l_nat = -INFINITY, Di = 0.f;
+      if (row_ok) {
+        l_nat = p.lse[stat];
+        Di = p.dsum[stat];
+      }
+      const int lim = i - j0 - 32 * half;  // this thread's columns bb <= lim are causal-visible
+      uint32_t vm = lim >= 31 ? 0xffffffffu : (lim < 0 ? 0u : ((2u << lim) - 1u));
+      vm &= ~kpm;
+
+      mbar_wait(m1_done, ph);
+      tc_fence_after();
+      const float lse2 = (!row_ok || l_nat == -INFINITY) ? INFINITY : l_nat * 1.4426950408889634f;
+
+      uint32_t pw[16], dw[20];  // bf16x2 words of P[a, 32h..] and dS[a, 32h..] (+ 4 zero words for the band shift)
+      {
+        uint32_t sv[32], dpv[32], rv[64];
+        tmem_ld32(t_lane + FB_COL_S + 32 * half, sv);
+        tmem_ld32(t_lane + FB_COL_DP + 32 * half, dpv);
+        tmem_ld64(t_lane + FB_COL_R + 96 - 32 * quarter + 32 * half, rv);
+        tc_wait_ld();
+        skew_select(rv, shift);
+#pragma unroll
+        for (int bb = 0; bb < 32; bb += 2) {
+          float pr[2], dr[2];
+#pragma unroll
+          for (int e = 0; e < 2; ++e) {
+            const float x = __uint_as_float(sv[bb + e]) + __uint_as_float(rv[bb + e]);
+            float pe = fast_exp2(fmaf(x, cs, -lse2));
+            if (!((vm >> (bb + e)) & 1u)) pe = 0.f;
+            pr[e] = pe;
+            dr[e] = pe * (__uint_as_float(dpv[bb + e]) - Di) * p.scale;
+          }
+          __nv_bfloat162 ph2 = __floats2bfloat162_rn(pr[0], pr[1]);
+          __nv_bfloat162 dh2 = __floats2bfloat162_rn(dr[0], dr[1]);
+          pw[bb / 2] = *reinterpret_cast<uint32_t*>(&ph2);
+          dw[bb / 2] = *reinterpret_cast<uint32_t*>(&dh2);
+        }
+      }
+      // the previous step's reduce-adds must have left shared memory before P / dS (= staging 2) are rewritten
+      if (lane == 0) bulk_wait_read_all();
+      named_bar_sync(1, FB_COMPUTE_THREADS);
+      // P and dS rows: UMMA SWIZZLE_128B rows of 128 B (chunk kc of row a at position kc ^ (a & 7))
+      {
+        uint8_t* prow = sP + a * 128;
+        uint8_t* drow = sdS + a * 128;
+#pragma unroll
+        for (int n = 0; n < 4; ++n) {
+          const int pos = (((4 * half + n) ^ (a & 7))) << 4;
+          *reinterpret_cast<uint4*>(prow + pos) = make_uint4(pw[4 * n], pw[4 * n + 1], pw[4 * n + 2], pw[4 * n + 3]);
+          *reinterpret_cast<uint4*>(drow + pos) = make_uint4(dw[4 * n], dw[4 * n + 1], dw[4 * n + 2], dw[4 * n + 3]);
+        }
+      }
+      // dS in band coordinates: shift right by win_o (0..7) elements inside a 40-element span.  Chunk 4 of
+      // the lower half and chunk 0 of the upper half are the same 16 bytes: both sides write only their own
+      // elements there (2-byte stores), every other chunk is written whole.
+      {
+        dw[16] = dw[17] = dw[18] = dw[19] = 0u;
+        const uint32_t on4 = win_o & 4, on2 = win_o & 2;
+#pragma unroll
+        for (int w = 19; w >= 0; --w) dw[w] = sel_b32(w >= 2 ? dw[w - 2] : 0u, dw[w], on4);
+#pragma unroll
+        for (int w = 19; w >= 0; --w) dw[w] = sel_b32(w >= 1 ? dw[w - 1] : 0u, dw[w], on2);
+        const uint32_t hs = (win_o & 1) ? 16u : 0u;
+#pragma unroll
+        for (int w = 19; w >= 0; --w) dw[w] = __funnelshift_l(w >= 1 ? dw[w - 1] : 0u, dw[w], hs);
+        auto chunk_ptr = [&](int q) -> uint8_t* {
+          return sdSb + (q >> 3) * 16384 + a * 128 + (((q & 7) ^ (a & 7)) << 4);
+        };
+        const int shared_n = half == 0 ? 4 : 0;  // this span's chunk that is shared with the other half
+#pragma unroll
+        for (int n = 0; n < 5; ++n) {
+          uint8_t* dst = chunk_ptr(win_q0 + n);
+          if (n != shared_n) {
+            *reinterpret_cast<uint4*>(dst) = make_uint4(dw[4 * n], dw[4 * n + 1], dw[4 * n + 2], dw[4 * n + 3]);
+          } else {
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+              const bool mine = half == 0 ? (e < win_o) : (e >= win_o);
+              const uint32_t word = dw[4 * n + e / 2];
+              const uint16_t val = static_cast<uint16_t>((e & 1) ? (word >> 16) : (word & 0xFFFFu));
+              if (mine) *reinterpret_cast<uint16_t*>(dst + 2 * e) = val;
+            }
           }
         }
       }
-    }
-    fence_proxy_async_smem();
-    tc_fence_before();
-    __syncthreads();
-    if (tid == 0) {
+      fence_proxy_async_smem();
+      tc_fence_before();
+      mbar_arrive(a_done);
+
+      // dQ tile and dE tile: TMEM -> padded fp32 rows in shared memory -> one TMA reduce-add per 32 rows
+      const int e0 = p.max_seq - FB_BM - (i0 - j0);
+      mbar_wait(m2q_done, ph);
       tc_fence_after();
-      const uint32_t acc0 = st > 0 ? 1u : 0u;
-#pragma unroll
-      for (int k = 0; k < 8; ++k)  // dV += P^T dO
-        umma_bf16(tmem_base + FB_COL_DV, make_smem_desc_sw128(p_addr + k * 2048, 16384, 1024),
-                  make_smem_desc_sw128(do_addr + k * 2048, 8192, 1024), idesc_tt, (k > 0) ? 1u : acc0);
-#pragma unroll
-      for (int k = 0; k < 8; ++k)  // dK += dS^T Q
-        umma_bf16(tmem_base + FB_COL_DK, make_smem_desc_sw128(ds_addr + k * 2048, 16384, 1024),
-                  make_smem_desc_sw128(q_addr + k * 2048, 8192, 1024), idesc_tt, (k > 0) ? 1u : acc0);
-#pragma unroll
-      for (int k = 0; k < 4; ++k)  // dQ_tile = dS K
-        umma_bf16(tmem_base + FB_COL_DQ, make_smem_desc_sw128(ds_addr + k * 32, 16, 1024),
-                  make_smem_desc_sw128(k_addr + k * 2048, 8192, 1024), idesc_nt, k > 0);
-#pragma unroll
-      for (int k = 0; k < 12; ++k)  // dQ_tile += dSb Eband
-        umma_bf16(tmem_base + FB_COL_DQ,
-                  make_smem_desc_sw128(dsb_addr + (k >> 2) * 16384 + (k & 3) * 32, 16, 1024),
-                  make_smem_desc_sw128(e_addr + k * 2048, 8192, 1024), idesc_nt, 1u);
-#pragma unroll
-      for (int k = 0; k < 8; ++k)  // dE_tile[0:128] = dSb[:, 0:128]^T Q
-        umma_bf16(tmem_base + FB_COL_DE_LO, make_smem_desc_sw128(dsb_addr + k * 2048, 16384, 1024),
-                  make_smem_desc_sw128(q_addr + k * 2048, 8192, 1024), idesc_tt, k > 0);
-#pragma unroll
-      for (int k = 0; k < 8; ++k)  // dE_tile[128:192] = dSb[:, 128:192]^T Q (lanes 64..127 unused)
-        umma_bf16(tmem_base + FB_COL_DE_HI, make_smem_desc_sw128(dsb_addr + 32768 + k * 2048, 16384, 1024),
-                  make_smem_desc_sw128(q_addr + k * 2048, 8192, 1024), idesc_tt, k > 0);
-      umma_commit(m2_done);
+      stage_row<HC>(t_lane + FB_COL_DQ + half * HC, reinterpret_cast<float*>(stg0 + a * STG) + half * HC);
+      mbar_wait(m2e_done, ph);  // also: dV / dK MMAs have retired, so the P / dS area is free for staging
+      tc_fence_after();
+      stage_row<HC>(t_lane + FB_COL_DE_LO + half * HC, reinterpret_cast<float*>(stg1 + a * STG) + half * HC);
+      if (quarter < 2)
+        stage_row<HC>(t_lane + FB_COL_DE_HI + half * HC, reinterpret_cast<float*>(stg2 + a * STG) + half * HC);
+      tc_fence_before();
+      mbar_arrive(b_done);  // this step's TMEM tiles are consumed
+      fence_proxy_async_smem();
+      named_bar_sync(1, FB_COMPUTE_THREADS);  // staging complete (both column halves of every row)
+      if (lane == 0) {
+        const int r0 = 32 * quarter;
+        if (half == 0) {
+          const int n = min(32, p.L - (i0 + r0));
+          if (n > 0)
+            bulk_reduce_add_f32(p.dq_ws + ((static_cast<int64_t>(b) * p.H + h) * p.L + i0 + r0) * (DH + 4),
+                                stg0 + r0 * STG, n * STG);
+        } else {
+          const int n = min(32, p.max_seq - (e0 + r0));
+          if (n > 0) bulk_reduce_add_f32(p.dE_ws + static_cast<int64_t>(e0 + r0) * (DH + 4), stg1 + r0 * STG, n * STG);
+          if (quarter < 2) {
+            const int n2 = min(32, p.max_seq - (e0 + 128 + r0));
+            if (n2 > 0)
+              bulk_reduce_add_f32(p.dE_ws + static_cast<int64_t>(e0 + 128 + r0) * (DH + 4), stg2 + r0 * STG, n2 * STG);
+          }
+        }
+        bulk_commit();
+      }
+      __syncwarp();
     }
-    __syncwarp();
-    mbar_wait(m2_done, st & 1);
+
+    // dK / dV: rows 0..63 of the accumulators (TMEM lanes 0..63: quarters 0 and 1), columns split by half
+    mbar_wait(m2b_done, (nsteps - 1) & 1);
     tc_fence_after();
-    if (tid == 0 && st + 1 < nsteps) load_step(st + 1);  // Q / dO / E buffers are free again
-    __syncwarp();
-
-    // dQ tile and dE tile: TMEM -> padded fp32 rows in shared memory -> one TMA reduce-add per 32 rows
-    const int e0 = p.max_seq - FB_BM - (i0 - j0);
-    stage_row<HC>(t_lane + FB_COL_DQ + half * HC, reinterpret_cast<float*>(stg0 + a * STG) + half * HC);
-    stage_row<HC>(t_lane + FB_COL_DE_LO + half * HC, reinterpret_cast<float*>(stg1 + a * STG) + half * HC);
-    if (quarter < 2)
-      stage_row<HC>(t_lane + FB_COL_DE_HI + half * HC, reinterpret_cast<float*>(stg2 + a * STG) + half * HC);
-    fence_proxy_async_smem();
-    tc_fence_before();
-    __syncthreads();  // staging complete (both column halves of every row)
-    if (lane == 0) {
-      const int r0 = 32 * quarter;
-      if (half == 0) {
-        const int n = min(32, p.L - (i0 + r0));
-        if (n > 0)
-          bulk_reduce_add_f32(p.dq_ws + ((static_cast<int64_t>(b) * p.H + h) * p.L + i0 + r0) * (DH + 4),
-                              stg0 + r0 * STG, n * STG);
-      } else {
-        const int n = min(32, p.max_seq - (e0 + r0));
-        if (n > 0) bulk_reduce_add_f32(p.dE_ws + static_cast<int64_t>(e0 + r0) * (DH + 4), stg1 + r0 * STG, n * STG);
-        if (quarter < 2) {
-          const int n2 = min(32, p.max_seq - (e0 + 128 + r0));
-          if (n2 > 0)
-            bulk_reduce_add_f32(p.dE_ws + static_cast<int64_t>(e0 + 128 + r0) * (DH + 4), stg2 + r0 * STG, n2 * STG);
+    if (quarter < 2) {
+      const int j = j0 + a;
+      const bool key_ok = j < p.L;
+      bf16* dkrow = p.dk + static_cast<int64_t>(b) * p.k_sb + static_cast<int64_t>(j) * p.k_sj + h * p.k_sh + half * HC;
+      bf16* dvrow = p.dv + static_cast<int64_t>(b) * p.v_sb + static_cast<int64_t>(j) * p.v_sj + h * p.v_sh + half * HC;
+#pragma unroll
+      for (int c0 = 0; c0 < HC; c0 += 8) {
+        uint32_t vk[8], vv[8];
+        tmem_ld8(t_lane + FB_COL_DK + half * HC + c0, vk);
+        tmem_ld8(t_lane + FB_COL_DV + half * HC + c0, vv);
+        tc_wait_ld();
+        if (key_ok) {
+          uint4 uk, uv;
+          __nv_bfloat162* hk = reinterpret_cast<__nv_bfloat162*>(&uk);
+          __nv_bfloat162* hv = reinterpret_cast<__nv_bfloat162*>(&uv);
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            hk[e] = __floats2bfloat162_rn(__uint_as_float(vk[2 * e]), __uint_as_float(vk[2 * e + 1]));
+            hv[e] = __floats2bfloat162_rn(__uint_as_float(vv[2 * e]), __uint_as_float(vv[2 * e + 1]));
+          }
+          *reinterpret_cast<uint4*>(dkrow + c0) = uk;
+          *reinterpret_cast<uint4*>(dvrow + c0) = uv;
         }
       }
-      bulk_commit();
-      bulk_wait_read_all();  // staging rows (and the P/dS area) may be overwritten afterwards
     }
-    __syncthreads();  // all TMEM tiles of this step have been read; shared staging is reusable
+    if (lane == 0) bulk_wait_all();
   }
-
-  // dK / dV: rows 0..63 of the accumulators (TMEM lanes 0..63: quarters 0 and 1), columns split by half
-  tc_fence_after();
-  if (quarter < 2) {
-    const int j = j0 + a;
-    const bool key_ok = j < p.L;
-    bf16* dkrow = p.dk + static_cast<int64_t>(b) * p.k_sb + static_cast<int64_t>(j) * p.k_sj + h * p.k_sh + half * HC;
-    bf16* dvrow = p.dv + static_cast<int64_t>(b) * p.v_sb + static_cast<int64_t>(j) * p.v_sj + h * p.v_sh + half * HC;
-#pragma unroll
-    for (int c0 = 0; c0 < HC; c0 += 8) {
-      uint32_t vk[8], vv[8];
-      tmem_ld8(t_lane + FB_COL_DK + half * HC + c0, vk);
-      tmem_ld8(t_lane + FB_COL_DV + half * HC + c0, vv);
-      tc_wait_ld();
-      if (key_ok) {
-        uint4 uk, uv;
-        __nv_bfloat162* hk = reinterpret_cast<__nv_bfloat162*>(&uk);
-        __nv_bfloat162* hv = reinterpret_cast<__nv_bfloat162*>(&uv);
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          hk[e] = __floats2bfloat162_rn(__uint_as_float(vk[2 * e]), __uint_as_float(vk[2 * e + 1]));
-          hv[e] = __floats2bfloat162_rn(__uint_as_float(vv[2 * e]), __uint_as_float(vv[2 * e + 1]));
-        }
-        *reinterpret_cast<uint4*>(dkrow + c0) = uk;
-        *reinterpret_cast<uint4*>(dvrow + c0) = uv;
-      }
-    }
-  }
-  if (lane == 0) bulk_wait_all();
   tc_fence_before();
   __syncthreads();
-  if (warp == 0) {
-    __syncwarp();
-    tmem_dealloc(tmem_base, FB_TMEM_COLS);
-  }
+  if (warp == FB_CONTROL_WARP) tmem_dealloc(tmem_base, FB_TMEM_COLS);
 }
 
 // dsum[b, h, i] = sum_c dO[b, i, h, c] * O[b, i, h, c]   (the "D" term of the softmax backward)
