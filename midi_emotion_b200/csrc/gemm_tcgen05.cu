@@ -22,7 +22,8 @@ void prof_end(cudaEvent_t e, cudaStream_t st);
 
 constexpr int G_BM = 128;
 constexpr int G_BK = 64;
-constexpr int G_THREADS = 192;  // warp0: TMA, warp1: MMA + TMEM alloc, warps 2..5: epilogue
+constexpr int G_EPI_THREADS = 256;  // warps 2..9: warp w reads TMEM lanes 32*(w&3).., column halves split by (w-2)/4
+constexpr int G_THREADS = 64 + G_EPI_THREADS;  // warp0: TMA, warp1: MMA + TMEM alloc, warps 2..9: epilogue
 
 struct GemmParams {
   int M, N, K;
@@ -41,7 +42,8 @@ struct GemmSmem {
   static constexpr int B_BYTES = BN * G_BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int STAGES = (BN >= 256) ? 4 : (BN >= 128 ? 6 : 8);
-  static constexpr int BAR_BYTES = (2 * STAGES + 4) * 8 + 16;
+  static constexpr int BIAS_BYTES = 2 * BN * 4;  // bias slice of the tile, double buffered with the accumulator
+  static constexpr int BAR_BYTES = (2 * STAGES + 4) * 8 + 16 + BIAS_BYTES;
   static constexpr int TOTAL = STAGES * STAGE_BYTES + BAR_BYTES + 1024;  // + alignment slack
 };
 
@@ -59,6 +61,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   uint64_t* tfull_bar = empty_bar + STAGES;   // [2]
   uint64_t* tempty_bar = tfull_bar + 2;       // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+  float* bias_s = reinterpret_cast<float*>(tmem_slot + 4);  // [2][BN]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   constexpr uint32_t TMEM_COLS = (2 * BN < 32) ? 32 : 2 * BN;
@@ -72,7 +75,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tfull_bar[s], 1);
-      mbar_init(&tempty_bar[s], 128);
+      mbar_init(&tempty_bar[s], G_EPI_THREADS);
     }
     fence_mbar_init();
   }
@@ -152,11 +155,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
   } else if (warp >= 2) {
     // ============================== epilogue ==============================
-    const int quarter = warp & 3;  // TMEM lane quarter this warp may access
+    const int quarter = warp & 3;        // TMEM lane quarter this warp may access
+    const int chalf = (warp - 2) >> 2;   // which half of the tile's columns
+    const int et = threadIdx.x - 64;     // 0..255
     const int row_in_tile = quarter * 32 + lane;
     const bool out_bf16 = p.out_dtype == ME_BF16;
     const bool vec_ok = out_bf16 ? (p.ldd % 8 == 0) : (p.ldd % 4 == 0);
+    const bool add_vec_ok = (p.ldd % 4 == 0);
     const bool mask_vec_ok = (p.ldmask % 8 == 0);
+    constexpr int HALF = BN / 2;
+    constexpr int CW = HALF >= 32 ? 32 : HALF;  // columns per TMEM load (BN = 32 -> 16)
     int it = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
       const int ks = tile % p.splits;
@@ -165,100 +173,121 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const int n0 = (mn % p.num_n_tiles) * BN;
       const int acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1;
-      mbar_wait(&tfull_bar[acc], acc_phase);
-      tc_fence_after();
+      const bool first_split = (ks == 0);
+      const bool use_bias = (p.flags & ME_EPI_BIAS) && first_split;
+      // the tile's bias slice goes through shared memory (one global load per thread instead of one per element)
+      float* bs = bias_s + acc * BN;
+      if (use_bias) {
+        for (int c = et; c < BN; c += G_EPI_THREADS) bs[c] = (n0 + c < p.N) ? __ldg(p.bias + n0 + c) : 0.f;
+      }
+      named_bar_sync(1, G_EPI_THREADS);
       const int m = m0 + row_in_tile;
       const bool row_ok = m < p.M;
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * BN;
+      mbar_wait(&tfull_bar[acc], acc_phase);
+      tc_fence_after();
 #pragma unroll 1
-      for (int c0 = 0; c0 < BN; c0 += 32) {
+      for (int c0 = chalf * HALF; c0 < (chalf + 1) * HALF; c0 += CW) {
         if (n0 + c0 >= p.N) break;  // warp-uniform
-        uint32_t r[32];
-        __syncwarp();
-        tmem_ld32(t_row + c0, r);
+        const int nb = n0 + c0;
+        const bool full = nb + CW <= p.N;
+        uint32_t r[CW];
+        if (CW == 32) tmem_ld32(t_row + c0, *reinterpret_cast<uint32_t(*)[32]>(r));
+        else tmem_ld16(t_row + c0, *reinterpret_cast<uint32_t(*)[16]>(r));
+        // operands of the epilogue are fetched while the TMEM load is in flight
+        float addv[CW];
+        uint32_t maskw[CW / 2];
+        const bool do_add = (p.flags & ME_EPI_ADD_F32) && first_split && row_ok;
+        const bool do_mask = (p.flags & ME_EPI_RELU_MASK) && row_ok;
+        if (do_add) {
+          const float* ap = p.addend + static_cast<int64_t>(m) * p.ldd + nb;
+          if (add_vec_ok && full) {
+#pragma unroll
+            for (int j = 0; j < CW / 4; ++j) {
+              const float4 t = __ldg(reinterpret_cast<const float4*>(ap) + j);
+              addv[4 * j] = t.x; addv[4 * j + 1] = t.y; addv[4 * j + 2] = t.z; addv[4 * j + 3] = t.w;
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < CW; ++j) addv[j] = (nb + j < p.N) ? ap[j] : 0.f;
+          }
+        }
+        if (do_mask) {
+          const bf16* mp = static_cast<const bf16*>(p.relu_mask) + static_cast<int64_t>(m) * p.ldmask + nb;
+          if (mask_vec_ok && full) {
+#pragma unroll
+            for (int j = 0; j < CW / 8; ++j) {
+              const uint4 u = __ldg(reinterpret_cast<const uint4*>(mp) + j);
+              maskw[4 * j] = u.x; maskw[4 * j + 1] = u.y; maskw[4 * j + 2] = u.z; maskw[4 * j + 3] = u.w;
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < CW / 2; ++j) {
+              const uint32_t lo = (nb + 2 * j < p.N) ? __bfloat16_as_ushort(mp[2 * j]) : 0u;
+              const uint32_t hi = (nb + 2 * j + 1 < p.N) ? __bfloat16_as_ushort(mp[2 * j + 1]) : 0u;
+              maskw[j] = lo | (hi << 16);
+            }
+          }
+        }
         tc_wait_ld();
         if (row_ok) {
-        const int nb = n0 + c0;
-        float v[32];
+          float v[CW];
 #pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
-        const bool first_split = (ks == 0);
-        if ((p.flags & ME_EPI_BIAS) && first_split) {
+          for (int j = 0; j < CW; ++j) v[j] = __uint_as_float(r[j]);
+          if (use_bias) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j)
-            if (nb + j < p.N) v[j] += __ldg(p.bias + nb + j);
-        }
-        if ((p.flags & ME_EPI_ADD_F32) && first_split) {
-          const float* ap = p.addend + static_cast<int64_t>(m) * p.ldd + nb;
-          if (p.ldd % 4 == 0 && nb + 32 <= p.N) {
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              const float4 t = __ldg(reinterpret_cast<const float4*>(ap) + j);
-              v[4 * j] += t.x; v[4 * j + 1] += t.y; v[4 * j + 2] += t.z; v[4 * j + 3] += t.w;
-            }
-          } else {
-#pragma unroll
-            for (int j = 0; j < 32; ++j)
-              if (nb + j < p.N) v[j] += ap[j];
+            for (int j = 0; j < CW; ++j) v[j] += bs[c0 + j];
           }
-        }
-        if (p.flags & ME_EPI_RELU) {
+          if (do_add) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
-        }
-        if (p.flags & ME_EPI_RELU_MASK) {
-          const bf16* mp = static_cast<const bf16*>(p.relu_mask) + static_cast<int64_t>(m) * p.ldmask + nb;
-          if (mask_vec_ok && nb + 32 <= p.N) {
+            for (int j = 0; j < CW; ++j) v[j] += addv[j];
+          }
+          if (p.flags & ME_EPI_RELU) {
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              const uint4 u = __ldg(reinterpret_cast<const uint4*>(mp) + j);
-              const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&u);
+            for (int j = 0; j < CW; ++j) v[j] = fmaxf(v[j], 0.f);
+          }
+          if (do_mask) {
 #pragma unroll
-              for (int e = 0; e < 4; ++e) {
-                const float2 f = __bfloat1622float2(h2[e]);
-                if (!(f.x > 0.f)) v[8 * j + 2 * e] = 0.f;
-                if (!(f.y > 0.f)) v[8 * j + 2 * e + 1] = 0.f;
+            for (int j = 0; j < CW / 2; ++j) {
+              // bf16 > 0  <=>  sign bit clear and magnitude bits non-zero
+              const uint32_t w = maskw[j];
+              if (!((w & 0x8000u) == 0u && (w & 0x7FFFu) != 0u)) v[2 * j] = 0.f;
+              if (!((w & 0x80000000u) == 0u && (w & 0x7FFF0000u) != 0u)) v[2 * j + 1] = 0.f;
+            }
+          }
+          if (p.splits > 1) {
+            float* dp = static_cast<float*>(p.D) + static_cast<int64_t>(m) * p.ldd + nb;
+#pragma unroll
+            for (int j = 0; j < CW; ++j)
+              if (nb + j < p.N) atomicAdd(dp + j, v[j]);
+          } else if (out_bf16) {
+            bf16* dp = static_cast<bf16*>(p.D) + static_cast<int64_t>(m) * p.ldd + nb;
+            if (vec_ok && full) {
+#pragma unroll
+              for (int j = 0; j < CW / 8; ++j) {
+                uint4 u;
+                __nv_bfloat162* h2 = reinterpret_cast<__nv_bfloat162*>(&u);
+#pragma unroll
+                for (int e = 0; e < 4; ++e) h2[e] = __floats2bfloat162_rn(v[8 * j + 2 * e], v[8 * j + 2 * e + 1]);
+                reinterpret_cast<uint4*>(dp)[j] = u;
               }
+            } else {
+#pragma unroll
+              for (int j = 0; j < CW; ++j)
+                if (nb + j < p.N) dp[j] = __float2bfloat16_rn(v[j]);
             }
           } else {
+            float* dp = static_cast<float*>(p.D) + static_cast<int64_t>(m) * p.ldd + nb;
+            if (vec_ok && full) {
 #pragma unroll
-            for (int j = 0; j < 32; ++j)
-              if (nb + j < p.N && !(__bfloat162float(mp[j]) > 0.f)) v[j] = 0.f;
-          }
-        }
-        if (p.splits > 1) {
-          float* dp = static_cast<float*>(p.D) + static_cast<int64_t>(m) * p.ldd + nb;
+              for (int j = 0; j < CW / 4; ++j)
+                reinterpret_cast<float4*>(dp)[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+            } else {
 #pragma unroll
-          for (int j = 0; j < 32; ++j)
-            if (nb + j < p.N) atomicAdd(dp + j, v[j]);
-        } else if (out_bf16) {
-          bf16* dp = static_cast<bf16*>(p.D) + static_cast<int64_t>(m) * p.ldd + nb;
-          if (vec_ok && nb + 32 <= p.N) {
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              uint4 u;
-              __nv_bfloat162* h2 = reinterpret_cast<__nv_bfloat162*>(&u);
-#pragma unroll
-              for (int e = 0; e < 4; ++e) h2[e] = __floats2bfloat162_rn(v[8 * j + 2 * e], v[8 * j + 2 * e + 1]);
-              reinterpret_cast<uint4*>(dp)[j] = u;
+              for (int j = 0; j < CW; ++j)
+                if (nb + j < p.N) dp[j] = v[j];
             }
-          } else {
-#pragma unroll
-            for (int j = 0; j < 32; ++j)
-              if (nb + j < p.N) dp[j] = __float2bfloat16_rn(v[j]);
           }
-        } else {
-          float* dp = static_cast<float*>(p.D) + static_cast<int64_t>(m) * p.ldd + nb;
-          if (vec_ok && nb + 32 <= p.N) {
-#pragma unroll
-            for (int j = 0; j < 8; ++j)
-              reinterpret_cast<float4*>(dp)[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-          } else {
-#pragma unroll
-            for (int j = 0; j < 32; ++j)
-              if (nb + j < p.N) dp[j] = v[j];
-          }
-        }
         }  // row_ok
       }
       __syncwarp();
@@ -322,9 +351,18 @@ int launch_gemm_bf16(const void* A, const void* B, void* D, int M, int N, int K,
   int splits = 1;
   if (force_splits > 0) splits = force_splits;
   else if (out_dtype == ME_F32 && !(flags & (ME_EPI_RELU | ME_EPI_RELU_MASK)) && num_kb >= 32) {
-    // split-K only where the epilogue is linear (weight gradients)
+    // split-K only where the epilogue is linear (weight gradients): pick the split count whose CTA count
+    // fills whole waves of SMs best (each split keeps at least 8 k-blocks)
     const int tiles = num_m_tiles * num_n_tiles;
-    while (tiles * splits * 2 <= sms && num_kb / (splits * 2) >= 8) splits *= 2;
+    if (tiles < sms) {
+      double best = 0.0;
+      for (int sp = 1; sp <= 16 && num_kb / sp >= 8; ++sp) {
+        const int ctas = tiles * sp;
+        const int waves = (ctas + sms - 1) / sms;
+        const double eff = static_cast<double>(ctas) / (static_cast<double>(waves) * sms);
+        if (eff > best + 0.02) { best = eff; splits = sp; }
+      }
+    }
   }
   if (splits > num_kb) splits = num_kb;
   ME_CHECK(splits == 1 || (out_dtype == ME_F32 && !(flags & (ME_EPI_RELU | ME_EPI_RELU_MASK))),
