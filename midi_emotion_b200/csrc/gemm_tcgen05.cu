@@ -341,8 +341,12 @@ int launch_gemm_bf16(const void* A, const void* B, void* D, int M, int N, int K,
   if (force_bn) bn = force_bn;
   else {
     const int min_bn = b_mn ? 128 : 32;
-    while (bn > min_bn && num_m_tiles * ((N + bn - 1) / bn) < sms) bn >>= 1;
-    if (b_mn && bn < 128) bn = 128;
+    if (a_mn && b_mn) {
+      bn = N > 128 ? 256 : 128;  // weight gradients: wide tiles + split-K beat narrow tiles (gemm_sweep.py)
+    } else {
+      while (bn > min_bn && num_m_tiles * ((N + bn - 1) / bn) < sms) bn >>= 1;
+      if (b_mn && bn < 128) bn = 128;
+    }
   }
   ME_CHECK(bn == 32 || bn == 64 || bn == 128 || bn == 256, "me_gemm_bf16: bad tile width %d", bn);
   ME_CHECK(!(b_mn && bn < 128), "me_gemm_bf16: MN-major B needs tile width >= 128");
@@ -353,15 +357,12 @@ int launch_gemm_bf16(const void* A, const void* B, void* D, int M, int N, int K,
   else if (out_dtype == ME_F32 && !(flags & (ME_EPI_RELU | ME_EPI_RELU_MASK)) && num_kb >= 32) {
     // split-K only where the epilogue is linear (weight gradients): pick the split count whose CTA count
     // fills whole waves of SMs best (each split keeps at least 8 k-blocks)
+    // measured on B200 (scripts/gemm_sweep.py): one wave of CTAs, as full as the split count allows
     const int tiles = num_m_tiles * num_n_tiles;
     if (tiles < sms) {
-      double best = 0.0;
-      for (int sp = 1; sp <= 16 && num_kb / sp >= 8; ++sp) {
-        const int ctas = tiles * sp;
-        const int waves = (ctas + sms - 1) / sms;
-        const double eff = static_cast<double>(ctas) / (static_cast<double>(waves) * sms);
-        if (eff > best + 0.02) { best = eff; splits = sp; }
-      }
+      splits = sms / tiles;
+      if (splits > num_kb / 8) splits = num_kb / 8;
+      if (splits < 1) splits = 1;
     }
   }
   if (splits > num_kb) splits = num_kb;
