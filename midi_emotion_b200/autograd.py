@@ -155,10 +155,24 @@ def run_backward(model, tokens, cond, a: _Acts, g_logits: torch.Tensor) -> List[
     tt = dict(device=dev, dtype=tdt)
     grads = {}
 
+    hook = getattr(model, "_grad_ready_hook", None)
+
+    def group(shapes):
+        """One flat fp32 buffer carved into gradient tensors (a data-parallel wrapper reduces it in one call)."""
+        sizes = [int(torch.Size(sh).numel()) for sh in shapes.values()]
+        padded = [(n + 3) // 4 * 4 for n in sizes]           # keep every tensor 16-byte aligned
+        flat = torch.empty(sum(padded), **f32)
+        out, off = {}, 0
+        for (name, sh), n, pn in zip(shapes.items(), sizes, padded):
+            out[name] = flat[off:off + n].view(sh)
+            off += pn
+        return flat, out
+
     last = a.layers[-1]
     # head: dW = g^T x, db = colsum(g), dx = g W
-    grads["fc.weight"] = torch.empty(V, d, **f32)
-    grads["fc.bias"] = torch.zeros(V, **f32)
+    flat_head, gh = group({"fc.weight": (V, d), "fc.bias": (V,)})
+    gh["fc.bias"].zero_()
+    grads.update(gh)
     d_x = torch.empty(M, d, **f32)
     _lib.call("me_colsum", ptr(g_logits), dtype, M, V, Vp, ptr(grads["fc.bias"]), stream)
     if dtype == ME_BF16:
@@ -171,6 +185,8 @@ def run_backward(model, tokens, cond, a: _Acts, g_logits: torch.Tensor) -> List[
                   0, None, None, None, 0, stream)
         _lib.call("me_gemm_f32", ptr(g_logits), ptr(wc["Wfc"]), ptr(d_x), M, d, V, Vp, d, d, 0, 1, 0, None, None,
                   None, 0, stream)
+    if hook is not None:
+        hook(flat_head)
 
     ws = {
         "g_a": torch.empty(M, d, **f32), "g_b": torch.empty(M, d, **f32), "g_T": torch.empty(M, d, **tt),
@@ -186,16 +202,12 @@ def run_backward(model, tokens, cond, a: _Acts, g_logits: torch.Tensor) -> List[
         act = a.layers[l]
         act["proj"] = ws["proj"]
         pre = f"enc_layers.{l}."
-        dWqkv = torch.empty(3 * d, d, **f32)
-        dbqkv = torch.empty(3 * d, **f32)
-        g = {
-            "dWqkv": dWqkv, "dbqkv": dbqkv, "dE": torch.empty(model.max_seq, dh, **f32),
-            "dWo": torch.empty(d, d, **f32), "dbo": torch.empty(d, **f32),
-            "dln1_w": torch.empty(d, **f32), "dln1_b": torch.empty(d, **f32),
-            "dW1": torch.empty(di, d, **f32), "db1": torch.empty(di, **f32),
-            "dW2": torch.empty(d, di, **f32), "db2": torch.empty(d, **f32),
-            "dln2_w": torch.empty(d, **f32), "dln2_b": torch.empty(d, **f32),
-        }
+        flat_l, g = group({
+            "dWqkv": (3 * d, d), "dbqkv": (3 * d,), "dE": (model.max_seq, dh),
+            "dWo": (d, d), "dbo": (d,), "dln1_w": (d,), "dln1_b": (d,),
+            "dW1": (di, d), "db1": (di,), "dW2": (d, di), "db2": (d,), "dln2_w": (d,), "dln2_b": (d,),
+        })
+        dWqkv, dbqkv = g["dWqkv"], g["dbqkv"]
         ba = _lib.LayerBwdArgs()
         ba.f = _layer_args(model, wc["layers"][l], lay, act, act["x_f32"], act["x_T"], a.keypad, a, l)
         ba.f.training = 1
@@ -215,15 +227,25 @@ def run_backward(model, tokens, cond, a: _Acts, g_logits: torch.Tensor) -> List[
         grads[pre + "layernorm1.weight"], grads[pre + "layernorm1.bias"] = g["dln1_w"], g["dln1_b"]
         grads[pre + "layernorm2.weight"], grads[pre + "layernorm2.bias"] = g["dln2_w"], g["dln2_b"]
         a.layers[l] = None  # free this layer's activations as soon as they are consumed
+        if hook is not None:
+            hook(flat_l)
 
     # input stage
-    d_emb = torch.zeros_like(model.embedding.weight)
-    grads["embedding.weight"] = d_emb
     cw0, cb0, cw1, cb1 = model._cond_params()
-    d_c = [torch.zeros_like(t) if t is not None else None for t in (cw0, cb0, cw1, cb1)]
+    shapes = {"emb": tuple(model.embedding.weight.shape)}
+    for i, t in enumerate((cw0, cb0, cw1, cb1)):
+        if t is not None:
+            shapes[f"c{i}"] = tuple(t.shape)
+    flat_in, gi = group(shapes)
+    flat_in.zero_()
+    d_emb = gi["emb"]
+    grads["embedding.weight"] = d_emb
+    d_c = [gi.get(f"c{i}") for i in range(4)]
     _lib.call("me_embed_backward", ptr(d_x), ptr(tokens), ptr(cond), B, L, d, model.d_condition, V, model.mode,
               model.pad_token, a.p, a.seed << 8 | 0xFF, ptr(d_emb), ptr(d_c[0]), ptr(d_c[1]), ptr(d_c[2]),
               ptr(d_c[3]), stream)
+    if hook is not None:
+        hook(flat_in)
     if model.continuous_token:
         grads["fc_condition.0.weight"], grads["fc_condition.0.bias"] = d_c[0], d_c[1]
         grads["fc_condition.1.weight"], grads["fc_condition.1.bias"] = d_c[2], d_c[3]

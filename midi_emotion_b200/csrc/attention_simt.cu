@@ -300,8 +300,14 @@ int attn_check(const me_attn_args* a, const char* who) {
   return 0;
 }
 
+int launch_attn_decode(const me_attn_args* a);
+
 int launch_attn_fwd_simt(const me_attn_args* a) {
   if (attn_check(a, "me_attention_forward")) return 1;
+  // single query row per sequence over a bf16 KV cache: the HBM-streaming decode kernel
+  if (a->dtype == ME_BF16 && a->Lq == 1 && a->lse == nullptr && (a->dh == 32 || a->dh == 48 || a->dh == 64) &&
+      a->q_sb % 8 == 0 && a->q_sh % 8 == 0 && a->o_sb % 2 == 0)
+    return launch_attn_decode(a);
   AttnP p = to_p(a);
   dim3 grid((a->Lq + AT_WARPS - 1) / AT_WARPS, a->H, a->B);
   cudaStream_t st = static_cast<cudaStream_t>(a->stream);

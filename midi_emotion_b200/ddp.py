@@ -44,23 +44,47 @@ def allreduce_mean_(tensors: Iterable[torch.Tensor], group=None, bucket_mb: floa
 
 
 class DataParallel:
-    """Minimal DDP wrapper: identical initial weights (broadcast from rank 0), `sync_gradients()`
-    after `loss.backward()` and before clipping / the optimiser step (train.py:319-325 order)."""
+    """Minimal DDP wrapper: identical initial weights (broadcast from rank 0), gradient averaging
+    overlapped with backward, `sync_gradients()` after `loss.backward()` and before clipping / the
+    optimiser step (train.py:319-325 order).
 
-    def __init__(self, model: torch.nn.Module, group=None, bucket_mb: float = 256.0):
+    The model's hand-written backward produces the gradients of one layer in one flat buffer and calls
+    `model._grad_ready_hook(flat)` as soon as they are enqueued; the hook starts an asynchronous NCCL
+    allreduce (AVG) of that buffer, which runs while the earlier layers' backward kernels execute.
+    `sync_gradients()` waits for those reductions and reduces, in buckets, whatever gradient did not live
+    in a hooked buffer (e.g. when gradients were accumulated into pre-existing `.grad` tensors)."""
+
+    def __init__(self, model: torch.nn.Module, group=None, bucket_mb: float = 256.0, overlap: bool = True):
         self.module = model
         self.group = group
         self.bucket_mb = bucket_mb
-        if dist.is_initialized() and dist.get_world_size(group) > 1:
+        self._pending = []
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        if self.world > 1:
             with torch.no_grad():
                 for p in model.parameters():
                     dist.broadcast(p, src=0, group=group)
+            if overlap and hasattr(model, "_param_list") and next(model.parameters()).is_cuda:
+                model._grad_ready_hook = self._on_grads_ready
 
     def __call__(self, *a, **kw):
         return self.module(*a, **kw)
 
+    def _on_grads_ready(self, flat: torch.Tensor) -> None:
+        work = dist.all_reduce(flat, op=dist.ReduceOp.AVG, group=self.group, async_op=True)
+        self._pending.append((flat, work))
+
     def sync_gradients(self) -> None:
-        allreduce_mean_([p.grad for p in self.module.parameters()], self.group, self.bucket_mb)
+        if self.world == 1:
+            return
+        done = set()
+        for flat, work in self._pending:
+            work.wait()
+            done.add(flat.untyped_storage().data_ptr())
+        self._pending = []
+        rest = [p.grad for p in self.module.parameters()
+                if p.grad is not None and p.grad.untyped_storage().data_ptr() not in done]
+        allreduce_mean_(rest, self.group, self.bucket_mb)
 
 
 def shard_batch(n_items: int, rank: int, world: int):
