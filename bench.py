@@ -59,7 +59,7 @@ class ClockSampler:
         try:
             self.fh = open(self.path, "w")
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "100", "-i", str(self.index)], stdout=self.fh,
+                                          "-lms", "50", "-i", str(self.index)], stdout=self.fh,
                                          stderr=subprocess.DEVNULL)
         except Exception:
             self.proc = None
@@ -154,17 +154,61 @@ def run_reference(args, rank):
 
 
 # ----------------------------------------------------------------------------------------------
+# decode leg (BASELINE configs[3]): KV-cache step at B=256, T=2048, measured mid-sequence
+# ----------------------------------------------------------------------------------------------
+def decode_leg(model, peaks, B=256, T=2048, t_mid=1024, steps=20):
+    """Step latency is linear in the prefix length, so the mid-sequence step is the average step of a
+    full 2048-token generation.  HBM-algorithmic bytes: weights once + K/V rows of every sequence."""
+    from midi_emotion_b200 import KVCacheDecoder
+    model.eval()
+    opt_free = torch.cuda.empty_cache
+    opt_free()
+    dec = KVCacheDecoder(model, B, max_len=T, precision="bf16")
+    dev = next(model.parameters()).device
+    g = torch.Generator(device=dev).manual_seed(5)
+    cond = torch.rand(B, 2, device=dev, generator=g) * 2 - 1
+    tok = torch.randint(1, CFG2["vocab_size"], (B, 2), device=dev, generator=g)
+    dec.prefill(tok, cond)
+    for c in dec.k_cache + dec.v_cache:
+        c.normal_(0, 0.5, generator=g)
+    nxt = torch.randint(1, CFG2["vocab_size"], (B,), device=dev, generator=g)
+    for _ in range(3):
+        dec.step(nxt)                       # eager step, graph capture, first replay
+    dec.t_dev.fill_(t_mid)
+    dec.t_host = t_mid
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        logits = dec.step(nxt)
+        nxt = logits.argmax(-1)             # greedy feedback keeps the loop honest (device side, no sync)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    d, NL, V = CFG2["d_model"], CFG2["n_layer"], CFG2["vocab_size"]
+    kv = B * NL * 2 * (t_mid + steps / 2) * d * 2
+    w = NL * 12 * d * d * 2 + d * V * 2
+    gbs = (kv + w) / ms / 1e6
+    model.train()
+    return {"metric": "decode tokens/sec @ seq2048 (KV cache, B=256, mid-sequence step t=1024)",
+            "value": B / ms * 1e3, "unit": "tokens/s", "ms_per_step": ms, "batch": B, "max_len": T,
+            "roofline": {"bound": "hbm", "achieved": gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                         "frac": gbs / peaks["hbm_gbs"], "algorithmic_bytes_per_step": kv + w}}
+
+
+# ----------------------------------------------------------------------------------------------
 # this repo's arm
 # ----------------------------------------------------------------------------------------------
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--batch", type=int, default=BATCH_PER_GPU, help="sequences per GPU")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--attn", default="auto", choices=["auto", "simt", "tensor"])
+    ap.add_argument("--no-decode", action="store_true", help="skip the KV-cache decode measurement (configs[3])")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -287,6 +331,8 @@ def main():
                          "whole_step_tflops": value * fpt / 1e12,
                          "whole_step_frac": value * fpt / 1e12 / peaks["tf_sustained"] / world},
         }
+        if world == 1 and not args.no_decode:
+            line["decode"] = decode_leg(model, peaks)
         if world == 1 and not args.no_cpu_baseline:
             tps, cms, threads = cpu_train_tokens_per_s(steps=2, warmup=1, B=1)
             line["cpu_baseline"] = {"value": tps, "unit": "tokens/s", "cores": threads, "kind": "port",

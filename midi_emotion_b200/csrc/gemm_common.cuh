@@ -1,0 +1,125 @@
+// Pieces shared by the 1-CTA and the 2-CTA tcgen05 GEMM kernels.
+#pragma once
+#include "common.cuh"
+#include "../../include/midi_emotion_b200.h"
+
+namespace me {
+
+cudaEvent_t prof_begin(double flops, cudaStream_t st);
+void prof_end(cudaEvent_t e, cudaStream_t st);
+
+struct GemmParams {
+  int M, N, K;
+  int ldd, ldmask;
+  int flags, out_dtype;
+  int num_m_tiles, num_n_tiles, splits, kb_per_split, num_kb;
+  const float* bias;
+  const float* addend;
+  const void* relu_mask;
+  void* D;
+};
+
+
+// One chunk of CW accumulator columns of row m (already loaded from TMEM into r): bias / residual / ReLU /
+// ReLU-mask, then bf16 or fp32 stores (16-byte vectors when the row pitch allows) or split-K atomics.
+// addv / maskw were fetched by the caller while the TMEM load was in flight.
+template <int CW>
+__device__ __forceinline__ void gemm_epilogue_chunk(const GemmParams& p, const uint32_t (&r)[CW], const float* bs,
+                                                    const float (&addv)[CW], const uint32_t (&maskw)[CW / 2],
+                                                    bool use_bias, bool do_add, bool do_mask, int m, int nb,
+                                                    bool full, bool vec_ok) {
+  float v[CW];
+#pragma unroll
+  for (int j = 0; j < CW; ++j) v[j] = __uint_as_float(r[j]);
+  if (use_bias) {
+#pragma unroll
+    for (int j = 0; j < CW; ++j) v[j] += bs[j];
+  }
+  if (do_add) {
+#pragma unroll
+    for (int j = 0; j < CW; ++j) v[j] += addv[j];
+  }
+  if (p.flags & ME_EPI_RELU) {
+#pragma unroll
+    for (int j = 0; j < CW; ++j) v[j] = fmaxf(v[j], 0.f);
+  }
+  if (do_mask) {
+#pragma unroll
+    for (int j = 0; j < CW / 2; ++j) {
+      const uint32_t w = maskw[j];  // bf16 > 0  <=>  sign bit clear and magnitude bits non-zero
+      if (!((w & 0x8000u) == 0u && (w & 0x7FFFu) != 0u)) v[2 * j] = 0.f;
+      if (!((w & 0x80000000u) == 0u && (w & 0x7FFF0000u) != 0u)) v[2 * j + 1] = 0.f;
+    }
+  }
+  if (p.splits > 1) {
+    float* dp = static_cast<float*>(p.D) + static_cast<int64_t>(m) * p.ldd + nb;
+#pragma unroll
+    for (int j = 0; j < CW; ++j)
+      if (nb + j < p.N) atomicAdd(dp + j, v[j]);
+  } else if (p.out_dtype == ME_BF16) {
+    bf16* dp = static_cast<bf16*>(p.D) + static_cast<int64_t>(m) * p.ldd + nb;
+    if (vec_ok && full) {
+#pragma unroll
+      for (int j = 0; j < CW / 8; ++j) {
+        uint4 u;
+        __nv_bfloat162* h2 = reinterpret_cast<__nv_bfloat162*>(&u);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) h2[e] = __floats2bfloat162_rn(v[8 * j + 2 * e], v[8 * j + 2 * e + 1]);
+        reinterpret_cast<uint4*>(dp)[j] = u;
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < CW; ++j)
+        if (nb + j < p.N) dp[j] = __float2bfloat16_rn(v[j]);
+    }
+  } else {
+    float* dp = static_cast<float*>(p.D) + static_cast<int64_t>(m) * p.ldd + nb;
+    if (vec_ok && full) {
+#pragma unroll
+      for (int j = 0; j < CW / 4; ++j)
+        reinterpret_cast<float4*>(dp)[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+    } else {
+#pragma unroll
+      for (int j = 0; j < CW; ++j)
+        if (nb + j < p.N) dp[j] = v[j];
+    }
+  }
+}
+
+// Fetch the residual addend / ReLU-mask words of one chunk (issued before the TMEM wait).
+template <int CW>
+__device__ __forceinline__ void gemm_epilogue_prefetch(const GemmParams& p, float (&addv)[CW], uint32_t (&maskw)[CW / 2],
+                                                       bool do_add, bool do_mask, int m, int nb, bool full) {
+  if (do_add) {
+    const float* ap = p.addend + static_cast<int64_t>(m) * p.ldd + nb;
+    if ((p.ldd % 4 == 0) && full) {
+#pragma unroll
+      for (int j = 0; j < CW / 4; ++j) {
+        const float4 t = __ldg(reinterpret_cast<const float4*>(ap) + j);
+        addv[4 * j] = t.x; addv[4 * j + 1] = t.y; addv[4 * j + 2] = t.z; addv[4 * j + 3] = t.w;
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < CW; ++j) addv[j] = (nb + j < p.N) ? ap[j] : 0.f;
+    }
+  }
+  if (do_mask) {
+    const bf16* mp = static_cast<const bf16*>(p.relu_mask) + static_cast<int64_t>(m) * p.ldmask + nb;
+    if ((p.ldmask % 8 == 0) && full) {
+#pragma unroll
+      for (int j = 0; j < CW / 8; ++j) {
+        const uint4 u = __ldg(reinterpret_cast<const uint4*>(mp) + j);
+        maskw[4 * j] = u.x; maskw[4 * j + 1] = u.y; maskw[4 * j + 2] = u.z; maskw[4 * j + 3] = u.w;
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < CW / 2; ++j) {
+        const uint32_t lo = (nb + 2 * j < p.N) ? __bfloat16_as_ushort(mp[2 * j]) : 0u;
+        const uint32_t hi = (nb + 2 * j + 1 < p.N) ? __bfloat16_as_ushort(mp[2 * j + 1]) : 0u;
+        maskw[j] = lo | (hi << 16);
+      }
+    }
+  }
+}
+
+}  // namespace me

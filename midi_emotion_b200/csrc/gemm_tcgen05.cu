@@ -12,29 +12,14 @@
 //
 // Both operands may be K-major ([rows, K], K contiguous) or MN-major ([K, rows], rows contiguous);
 // the latter feeds dgrad (B = W as stored) and wgrad (A = dY^T, B = X^T) without transposes.
-#include "common.cuh"
-#include "../../include/midi_emotion_b200.h"
+#include "gemm_common.cuh"
 
 namespace me {
-
-cudaEvent_t prof_begin(double flops, cudaStream_t st);
-void prof_end(cudaEvent_t e, cudaStream_t st);
 
 constexpr int G_BM = 128;
 constexpr int G_BK = 64;
 constexpr int G_EPI_THREADS = 256;  // warps 2..9: warp w reads TMEM lanes 32*(w&3).., column halves split by (w-2)/4
 constexpr int G_THREADS = 64 + G_EPI_THREADS;  // warp0: TMA, warp1: MMA + TMEM alloc, warps 2..9: epilogue
-
-struct GemmParams {
-  int M, N, K;
-  int ldd, ldmask;
-  int flags, out_dtype;
-  int num_m_tiles, num_n_tiles, splits, kb_per_split, num_kb;
-  const float* bias;
-  const float* addend;
-  const void* relu_mask;
-  void* D;
-};
 
 template <int BN>
 struct GemmSmem {
@@ -321,6 +306,10 @@ static int launch_one(const CUtensorMap& tmA, const CUtensorMap& tmB, const Gemm
   return 0;
 }
 
+int launch_gemm_bf16_pair(const void* A, const void* B, void* D, int M, int N, int K, int lda, int ldb, int ldd,
+                          int a_mn, int b_mn, int out_dtype, int flags, const float* bias, const float* addend,
+                          const void* relu_mask, int ldmask, int force_splits, cudaStream_t st);
+
 int launch_gemm_bf16(const void* A, const void* B, void* D, int M, int N, int K, int lda, int ldb, int ldd,
                      int a_mn, int b_mn, int out_dtype, int flags, const float* bias, const float* addend,
                      const void* relu_mask, int ldmask, int force_bn, int force_splits, cudaStream_t st) {
@@ -334,6 +323,13 @@ int launch_gemm_bf16(const void* A, const void* B, void* D, int M, int N, int K,
   ME_CHECK(!(a_mn && !b_mn), "me_gemm_bf16: (A MN-major, B K-major) is not instantiated");
   ME_CHECK(me_device_is_sm100(), "me_gemm_bf16: tcgen05 path needs an sm_100 device");
 
+  // CTA-pair kernel (256 x 256 tiles, cta_group::2) whenever the problem fills the machine with them
+  if (force_bn == 0 || force_bn == 512) {
+    const int rc = launch_gemm_bf16_pair(A, B, D, M, N, K, lda, ldb, ldd, a_mn, b_mn, out_dtype, flags, bias, addend,
+                                         relu_mask, ldmask, force_bn == 512 ? (force_splits > 0 ? force_splits : -1) : 0, st);
+    if (rc >= 0) return rc;
+    ME_CHECK(force_bn != 512, "me_gemm_bf16: the CTA-pair kernel does not take this shape");
+  }
   const int sms = sm_count();
   const int num_m_tiles = (M + G_BM - 1) / G_BM;
   // tile width: widest tile that still yields >= ~1 wave of CTAs

@@ -405,3 +405,54 @@ def test_attention_tensor_core_backward(B, H, L, dh, pad):
     g_si, dE_si = _run_attention_backward(_lib.ATTN_SIMT, a, qkv, out, lse, dout, B, H, L, dh)
     assert rel_err(g_tc.float(), g_si.float()) < tol
     assert rel_err(dE_tc, dE_si) < tol
+
+
+PAIR_SHAPES = [
+    # M, N, K, a_mn, b_mn, splits
+    (512, 512, 128, 0, 0, 0),
+    (256, 256, 64, 0, 0, 0),
+    (1000, 1007, 96, 0, 0, 0),       # ragged M, N, K
+    (2048, 2304, 768, 0, 0, 0),
+    (777, 768, 3072, 0, 1, 0),       # dgrad
+    (768, 3072, 1024, 1, 1, 2),      # wgrad, split-K
+    (1007, 96, 300, 1, 1, 1),        # narrow N forced through the pair kernel
+]
+
+
+@pytest.mark.parametrize("M,N,K,a_mn,b_mn,splits", PAIR_SHAPES)
+def test_gemm_tcgen05_cta_pair_matches_fp32(M, N, K, a_mn, b_mn, splits):
+    A, B, As, Bs = _operands(M, N, K, a_mn, b_mn, seed=11)
+    want = A.float() @ B.float().t()
+    got = gemm_bf16(As, Bs, M, N, K, a_mn, b_mn, ME_F32, tile_n=512, splits=splits)
+    torch.cuda.synchronize()
+    assert torch.isfinite(got).all()
+    assert rel_err(got, want) < 1e-5, rel_err(got, want)
+
+
+@pytest.mark.parametrize("flags", ["bias_relu", "bias_add", "mask"])
+def test_gemm_tcgen05_cta_pair_epilogues(flags):
+    M, N, K = 520, 768, 256
+    A, B, As, Bs = _operands(M, N, K, 0, 0, seed=13)
+    bias = torch.randn(N, device="cuda")
+    addend = torch.randn(M, N, device="cuda")
+    mask = torch.randn(M, N, device="cuda").to(torch.bfloat16)
+    want = A.float() @ B.float().t()
+    f, kw = 0, {}
+    if "bias" in flags:
+        f |= _lib.EPI_BIAS
+        want = want + bias
+        kw["bias"] = bias
+    if "add" in flags:
+        f |= _lib.EPI_ADD_F32
+        want = want + addend
+        kw["addend"] = addend
+    if "relu" in flags:
+        f |= _lib.EPI_RELU
+        want = want.relu()
+    if flags == "mask":
+        f |= _lib.EPI_RELU_MASK
+        want = torch.where(mask.float() > 0, want, torch.zeros_like(want))
+        kw["mask"] = mask
+    got = gemm_bf16(As, Bs, M, N, K, 0, 0, ME_BF16, flags=f, tile_n=512, **kw)
+    torch.cuda.synchronize()
+    assert rel_err(got.float(), want) < 3e-3
