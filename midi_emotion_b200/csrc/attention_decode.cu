@@ -2,9 +2,9 @@
 //
 // HBM-bound: per (batch, head) the step streams t+1 rows of K and V once (2 * (t+1) * dh * 2 bytes); the
 // matching rows of E (shared by every batch/head, 256 KB per layer) come out of L2.
-// One CTA per (batch, head), 8 warps, lane = key: every lane reads whole 128-byte rows with 16-byte loads
-// (24 independent loads in flight per key), keeps its own running (max, sum, o[dh]) and the partial
-// states are merged once at the end (warp butterfly, then across warps through shared memory).
+// One CTA per (batch, head), 8 warps, four lanes per key (each owns a quarter of the row's 16-byte chunks),
+// every 4-lane group keeps its own running (max, sum, o) and the partial states are merged once at the
+// end (warp butterfly over the key slots, then across warps through shared memory).
 // The position comes from device memory so the launch is CUDA-graph friendly.
 #include "common.cuh"
 #include "../../include/midi_emotion_b200.h"
@@ -21,19 +21,21 @@ struct AdParams {
   float scale_log2;
 };
 
-// a row of DH bf16 as DH/8 raw 16-byte words; conversion to fp32 happens at the point of use so that the
-// loads of K, E and V rows of a key are all in flight together
-template <int DH>
-__device__ __forceinline__ void load_row_raw(const bf16* __restrict__ row, uint4 (&r)[DH / 8]) {
-#pragma unroll
-  for (int c = 0; c < DH / 8; ++c) r[c] = __ldg(reinterpret_cast<const uint4*>(row) + c);
-}
 __device__ __forceinline__ float bf_lo(uint32_t w) { return __uint_as_float(w << 16); }
 __device__ __forceinline__ float bf_hi(uint32_t w) { return __uint_as_float(w & 0xFFFF0000u); }
-template <int DH>
-__device__ __forceinline__ void dot_row(const float (&qf)[DH], const uint4 (&r)[DH / 8], float& s0, float& s1) {
+
+// Four lanes share one key: lane g = lane & 3 owns the 16-byte chunks {g, g + 4, ...} of the 128-byte rows
+// (so the 4 lanes of a key read 64 contiguous bytes per load instruction), i.e. NC = DH/32 chunks of 8 dims.
+template <int NC>
+__device__ __forceinline__ void load_chunks(const bf16* __restrict__ row, int g, uint4 (&r)[NC]) {
 #pragma unroll
-  for (int c = 0; c < DH / 8; ++c) {
+  for (int c = 0; c < NC; ++c) r[c] = __ldg(reinterpret_cast<const uint4*>(row) + g + 4 * c);
+}
+template <int NC>
+__device__ __forceinline__ float dot_chunks(const float (&qf)[NC * 8], const uint4 (&r)[NC]) {
+  float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+  for (int c = 0; c < NC; ++c) {
     const uint32_t w[4] = {r[c].x, r[c].y, r[c].z, r[c].w};
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
@@ -41,27 +43,38 @@ __device__ __forceinline__ void dot_row(const float (&qf)[DH], const uint4 (&r)[
       s1 = fmaf(qf[c * 8 + 2 * e + 1], bf_hi(w[e]), s1);
     }
   }
+  return s0 + s1;
 }
 
-template <int DH>
-__global__ void __launch_bounds__(AD_WARPS * 32)
+// DH in {32, 64, 128}: rows are split into 16-byte chunks dealt round-robin to the 4 lanes of a key.
+// DH = 48 (6 chunks) is handled by the DH = 64 instantiation with the tail chunks predicated off.
+template <int DHP, int DH>
+__global__ void __launch_bounds__(AD_WARPS * 32, 2)
 attn_decode_kernel(const bf16* __restrict__ q, const bf16* __restrict__ k, const bf16* __restrict__ v,
                    const bf16* __restrict__ E, bf16* __restrict__ out, AdParams p) {
-  __shared__ float red[AD_WARPS][DH + 2];
+  constexpr int NC = DHP / 32;       // chunks per lane
+  constexpr int ND = NC * 8;         // dims per lane
+  __shared__ float red[AD_WARPS][DHP + 2];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int g = lane & 3, kslot = lane >> 2;            // chunk group, key slot inside the warp (0..7)
   const int h = blockIdx.x, b = blockIdx.y;
-  const int t = p.pos_dev ? *p.pos_dev : p.q_pos0;  // position of the query == index of the newest key
-  float qf[DH];
-  {
-    uint4 qr[DH / 8];
-    load_row_raw<DH>(q + b * p.q_sb + h * p.q_sh, qr);
+  const int t = p.pos_dev ? *p.pos_dev : p.q_pos0;      // position of the query == index of the newest key
+  // chunk c of this lane covers dims 8*(g + 4c) .. +7 ; for DH = 48 the chunks with g + 4c >= 6 do not exist
+  bool live[NC];
 #pragma unroll
-    for (int c = 0; c < DH / 8; ++c) {
-      const uint32_t w[4] = {qr[c].x, qr[c].y, qr[c].z, qr[c].w};
+  for (int c = 0; c < NC; ++c) live[c] = 8 * (g + 4 * c) < DH;
+  float qf[ND];
+  {
+    const bf16* qrow = q + b * p.q_sb + h * p.q_sh;
+#pragma unroll
+    for (int c = 0; c < NC; ++c) {
+      uint4 u = make_uint4(0, 0, 0, 0);
+      if (live[c]) u = __ldg(reinterpret_cast<const uint4*>(qrow) + g + 4 * c);
+      const uint32_t w[4] = {u.x, u.y, u.z, u.w};
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
-        qf[c * 8 + 2 * e] = bf_lo(w[e]);
-        qf[c * 8 + 2 * e + 1] = bf_hi(w[e]);
+        qf[c * 8 + 2 * e] = bf_lo(w[e]) * p.scale_log2;   // fold 1/sqrt(dh) * log2(e) into q
+        qf[c * 8 + 2 * e + 1] = bf_hi(w[e]) * p.scale_log2;
       }
     }
   }
@@ -71,71 +84,94 @@ attn_decode_kernel(const bf16* __restrict__ q, const bf16* __restrict__ k, const
   const uint8_t* kp = p.keypad ? p.keypad + b * p.keypad_ld : nullptr;
 
   float m = -INFINITY, l = 0.f;
-  float o[DH];
+  float o[ND];
 #pragma unroll
-  for (int c = 0; c < DH; ++c) o[c] = 0.f;
+  for (int c = 0; c < ND; ++c) o[c] = 0.f;
 
-  for (int j = warp * 32 + lane; j <= t; j += AD_WARPS * 32) {
-    if (kp && kp[j]) continue;
-    uint4 kr[DH / 8], er[DH / 8], vr[DH / 8];
-    load_row_raw<DH>(kb + j * p.k_sj, kr);
-    load_row_raw<DH>(Eb + static_cast<int64_t>(j) * DH, er);
-    load_row_raw<DH>(vb + j * p.v_sj, vr);
-    float s0 = 0.f, s1 = 0.f;
-    dot_row<DH>(qf, kr, s0, s1);
-    dot_row<DH>(qf, er, s0, s1);
-    const float x = (s0 + s1) * p.scale_log2;
-    if (x > m) {  // rescale the running state (rare once the maximum has settled)
-      const float a = fast_exp2(m - x);
-      l *= a;
+  for (int j0 = warp * 8; j0 <= t; j0 += AD_WARPS * 8) {
+    const int j = j0 + kslot;
+    const bool valid = j <= t && !(kp && kp[j]);
+    uint4 kr[NC], er[NC], vr[NC];
 #pragma unroll
-      for (int c = 0; c < DH; ++c) o[c] *= a;
-      m = x;
+    for (int c = 0; c < NC; ++c) {
+      kr[c] = er[c] = vr[c] = make_uint4(0, 0, 0, 0);
+      if (valid && live[c]) {
+        kr[c] = __ldg(reinterpret_cast<const uint4*>(kb + j * p.k_sj) + g + 4 * c);
+        er[c] = __ldg(reinterpret_cast<const uint4*>(Eb + static_cast<int64_t>(j) * DH) + g + 4 * c);
+        vr[c] = __ldg(reinterpret_cast<const uint4*>(vb + j * p.v_sj) + g + 4 * c);
+      }
     }
-    const float pj = fast_exp2(x - m);
-    l += pj;
+    float x = dot_chunks<NC>(qf, kr) + dot_chunks<NC>(qf, er);
+    x += __shfl_xor_sync(0xffffffffu, x, 1);
+    x += __shfl_xor_sync(0xffffffffu, x, 2);
+    if (valid) {
+      if (x > m) {  // rescale the running state (rare once the maximum has settled)
+        const float a = fast_exp2(m - x);
+        l *= a;
 #pragma unroll
-    for (int c = 0; c < DH / 8; ++c) {
-      const uint32_t w[4] = {vr[c].x, vr[c].y, vr[c].z, vr[c].w};
+        for (int c = 0; c < ND; ++c) o[c] *= a;
+        m = x;
+      }
+      const float pj = fast_exp2(x - m);
+      l += pj;
 #pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        o[c * 8 + 2 * e] = fmaf(pj, bf_lo(w[e]), o[c * 8 + 2 * e]);
-        o[c * 8 + 2 * e + 1] = fmaf(pj, bf_hi(w[e]), o[c * 8 + 2 * e + 1]);
+      for (int c = 0; c < NC; ++c) {
+        const uint32_t w[4] = {vr[c].x, vr[c].y, vr[c].z, vr[c].w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          o[c * 8 + 2 * e] = fmaf(pj, bf_lo(w[e]), o[c * 8 + 2 * e]);
+          o[c * 8 + 2 * e + 1] = fmaf(pj, bf_hi(w[e]), o[c * 8 + 2 * e + 1]);
+        }
       }
     }
   }
 
-  // merge the 32 lane states of the warp, then the warps of the block
-  const float wm = warp_max(m);
+  // merge the 8 key slots of the warp (lanes with equal g), then the warps of the block
+  float wm = m;
+#pragma unroll
+  for (int sft = 4; sft <= 16; sft <<= 1) wm = fmaxf(wm, __shfl_xor_sync(0xffffffffu, wm, sft));
   const float sc = (m == -INFINITY) ? 0.f : fast_exp2(m - wm);
-  l = warp_sum(l * sc);
+  l *= sc;
 #pragma unroll
-  for (int c = 0; c < DH; ++c) o[c] = warp_sum(o[c] * sc);
-  if (lane == 0) {
-    red[warp][DH] = wm;
-    red[warp][DH + 1] = l;
+  for (int c = 0; c < ND; ++c) o[c] *= sc;
 #pragma unroll
-    for (int c = 0; c < DH; ++c) red[warp][c] = o[c];
+  for (int sft = 4; sft <= 16; sft <<= 1) {
+    l += __shfl_xor_sync(0xffffffffu, l, sft);
+#pragma unroll
+    for (int c = 0; c < ND; ++c) o[c] += __shfl_xor_sync(0xffffffffu, o[c], sft);
+  }
+  if (kslot == 0) {
+    if (g == 0) {
+      red[warp][DHP] = wm;
+      red[warp][DHP + 1] = l;
+    }
+#pragma unroll
+    for (int c = 0; c < NC; ++c)
+#pragma unroll
+      for (int e = 0; e < 8; ++e) red[warp][8 * (g + 4 * c) + e] = o[c * 8 + e];
   }
   __syncthreads();
   if (warp == 0) {
     float gm = -INFINITY;
 #pragma unroll
-    for (int w = 0; w < AD_WARPS; ++w) gm = fmaxf(gm, red[w][DH]);
+    for (int w = 0; w < AD_WARPS; ++w) gm = fmaxf(gm, red[w][DHP]);
     float gl = 0.f;
-    float acc0 = 0.f, acc1 = 0.f;  // lane owns columns lane and lane + 32
+    float acc[DHP / 32];
+#pragma unroll
+    for (int c = 0; c < DHP / 32; ++c) acc[c] = 0.f;
 #pragma unroll
     for (int w = 0; w < AD_WARPS; ++w) {
-      const float wmx = red[w][DH];
-      const float s = (wmx == -INFINITY) ? 0.f : fast_exp2(wmx - gm);
-      gl += red[w][DH + 1] * s;
-      if (lane < DH) acc0 += red[w][lane] * s;
-      if (lane + 32 < DH) acc1 += red[w][lane + 32] * s;
+      const float wmx = red[w][DHP];
+      const float s2 = (wmx == -INFINITY) ? 0.f : fast_exp2(wmx - gm);
+      gl += red[w][DHP + 1] * s2;
+#pragma unroll
+      for (int c = 0; c < DHP / 32; ++c) acc[c] += red[w][lane + 32 * c] * s2;
     }
     const float inv = gl > 0.f ? 1.f / gl : 0.f;  // fully masked row -> 0
     bf16* orow = out + b * p.o_sb + h * DH;
-    if (lane < DH) orow[lane] = __float2bfloat16_rn(acc0 * inv);
-    if (lane + 32 < DH) orow[lane + 32] = __float2bfloat16_rn(acc1 * inv);
+#pragma unroll
+    for (int c = 0; c < DHP / 32; ++c)
+      if (lane + 32 * c < DH) orow[lane + 32 * c] = __float2bfloat16_rn(acc[c] * inv);
   }
 }
 
@@ -155,9 +191,9 @@ int launch_attn_decode(const me_attn_args* a) {
   const bf16* v = static_cast<const bf16*>(a->v);
   const bf16* E = static_cast<const bf16*>(a->E);
   bf16* out = static_cast<bf16*>(a->out);
-  if (a->dh == 64) attn_decode_kernel<64><<<grid, AD_WARPS * 32, 0, st>>>(q, k, v, E, out, p);
-  else if (a->dh == 48) attn_decode_kernel<48><<<grid, AD_WARPS * 32, 0, st>>>(q, k, v, E, out, p);
-  else attn_decode_kernel<32><<<grid, AD_WARPS * 32, 0, st>>>(q, k, v, E, out, p);
+  if (a->dh == 64) attn_decode_kernel<64, 64><<<grid, AD_WARPS * 32, 0, st>>>(q, k, v, E, out, p);
+  else if (a->dh == 48) attn_decode_kernel<64, 48><<<grid, AD_WARPS * 32, 0, st>>>(q, k, v, E, out, p);
+  else attn_decode_kernel<32, 32><<<grid, AD_WARPS * 32, 0, st>>>(q, k, v, E, out, p);
   ME_LAUNCH_CHECK();
   return 0;
 }
