@@ -74,46 +74,74 @@ __global__ void embed_fwd_kernel(const int64_t* __restrict__ tokens, const float
 }
 
 // dEmb[tok] += dx * sqrt(de) (pad rows skipped: Embedding(padding_idx=0) gets zero gradient);
-// fc_condition grads reduced over the sequence.  One block per (b, s) row, fp32 atomics.
-__global__ void embed_bwd_kernel(const float* __restrict__ dx, const int64_t* __restrict__ tokens,
-                                 const float* __restrict__ cond, int B, int L, int d, int dc, int V, int mode,
-                                 int pad_token, float p, uint64_t seed, float* __restrict__ d_emb,
-                                 float* __restrict__ d_cw0, float* __restrict__ d_cb0, float* __restrict__ d_cw1,
-                                 float* __restrict__ d_cb1) {
+// fc_condition grads reduced over the sequence.  A block owns EB_ROWS consecutive rows: the token part
+// goes out as 16-byte vector atomics (one per 4 columns), the condition part is summed over the block's
+// rows in registers first (one atomic per column per block instead of one per element).
+constexpr int EB_ROWS = 16;
+constexpr int EB_THREADS = 256;
+
+__global__ void __launch_bounds__(EB_THREADS)
+embed_bwd_kernel(const float* __restrict__ dx, const int64_t* __restrict__ tokens, const float* __restrict__ cond,
+                 int B, int L, int d, int dc, int V, int mode, int pad_token, float p, uint64_t seed,
+                 float* __restrict__ d_emb, float* __restrict__ d_cw0, float* __restrict__ d_cb0,
+                 float* __restrict__ d_cw1, float* __restrict__ d_cb1) {
   const bool ctoken = (mode == ME_COND_CONTINUOUS_TOKEN);
   const int Ls = ctoken ? L + 2 : L;
-  const int row = blockIdx.x;
-  const int b = row / Ls;
-  const int s = row - b * Ls;
+  const int64_t rows = static_cast<int64_t>(B) * Ls;
+  const int64_t r0 = static_cast<int64_t>(blockIdx.x) * EB_ROWS;
+  const int64_t r1 = min(rows, r0 + EB_ROWS);
   const int de = d - dc;
   const float scale = sqrtf(static_cast<float>(de));
   const float inv_keep = p > 0.f ? 1.f / (1.f - p) : 1.f;
-  const bool prefix = ctoken && s < 2;
-  int64_t tok = -1;
-  if (!prefix) tok = tokens[static_cast<int64_t>(b) * L + (ctoken ? s - 2 : s)];
-  float c0 = 0.f, c1 = 0.f;
-  if (mode == ME_COND_CONTINUOUS_CONCAT || prefix) {
-    c0 = cond[b * 2 + 0];
-    c1 = cond[b * 2 + 1];
-  }
-  for (int c = threadIdx.x; c < d; c += blockDim.x) {
-    float g = dx[static_cast<int64_t>(row) * d + c];
-    g *= dropout_scale(p, inv_keep, seed, static_cast<uint64_t>(row) * d + c);
-    if (prefix) {
-      if (s == 0) {
-        atomicAdd(&d_cw0[c], g * c0);
-        atomicAdd(&d_cb0[c], g);
-      } else {
-        atomicAdd(&d_cw1[c], g * c1);
-        atomicAdd(&d_cb1[c], g);
+  const uint32_t seed32 = dropout_seed32(seed);
+  const bool vec = (de % 4 == 0) && (d % 4 == 0);
+
+  // ---- token embedding columns (and the two prefix rows of continuous_token)
+  for (int64_t row = r0; row < r1; ++row) {
+    const int b = static_cast<int>(row / Ls);
+    const int s = static_cast<int>(row - static_cast<int64_t>(b) * Ls);
+    if (ctoken && s < 2) {  // Linear(1, d) prefix vectors: rare rows, element-wise atomics
+      const float cv = cond[b * 2 + s];
+      float* dw = s == 0 ? d_cw0 : d_cw1;
+      float* db = s == 0 ? d_cb0 : d_cb1;
+      for (int c = threadIdx.x; c < d; c += EB_THREADS) {
+        const float g = dx[row * d + c] * dropout_scale(p, inv_keep, seed, static_cast<uint64_t>(row) * d + c);
+        atomicAdd(&dw[c], g * cv);
+        atomicAdd(&db[c], g);
       }
-    } else if (c < de) {
-      if (tok != pad_token && tok >= 0 && tok < V) atomicAdd(&d_emb[tok * de + c], g * scale);
+      continue;
+    }
+    const int64_t tok = tokens[static_cast<int64_t>(b) * L + (ctoken ? s - 2 : s)];
+    if (tok == pad_token || tok < 0 || tok >= V) continue;
+    float* erow = d_emb + tok * de;
+    if (vec) {
+      for (int c = 4 * threadIdx.x; c < de; c += 4 * EB_THREADS) {
+        const float4 g = *reinterpret_cast<const float4*>(dx + row * d + c);
+        float dm[4];
+        dropout_scale4(p, inv_keep, seed32, static_cast<uint64_t>(row) * d + c, dm);
+        atomicAdd(reinterpret_cast<float4*>(erow + c),
+                  make_float4(g.x * dm[0] * scale, g.y * dm[1] * scale, g.z * dm[2] * scale, g.w * dm[3] * scale));
+      }
     } else {
-      const int j = c - de;
-      atomicAdd(&d_cw0[j * 2 + 0], g * c0);
-      atomicAdd(&d_cw0[j * 2 + 1], g * c1);
-      atomicAdd(&d_cb0[j], g);
+      for (int c = threadIdx.x; c < de; c += EB_THREADS)
+        atomicAdd(&erow[c], dx[row * d + c] * scale * dropout_scale(p, inv_keep, seed, static_cast<uint64_t>(row) * d + c));
+    }
+  }
+  // ---- concatenated condition columns: Linear(2, dc), summed over this block's rows
+  if (dc > 0) {
+    for (int j = threadIdx.x; j < dc; j += EB_THREADS) {
+      float a0 = 0.f, a1 = 0.f, ab = 0.f;
+      for (int64_t row = r0; row < r1; ++row) {
+        const int b = static_cast<int>(row / Ls);
+        const float g = dx[row * d + de + j] *
+                        dropout_scale(p, inv_keep, seed, static_cast<uint64_t>(row) * d + de + j);
+        a0 = fmaf(g, cond[b * 2 + 0], a0);
+        a1 = fmaf(g, cond[b * 2 + 1], a1);
+        ab += g;
+      }
+      atomicAdd(&d_cw0[j * 2 + 0], a0);
+      atomicAdd(&d_cw0[j * 2 + 1], a1);
+      atomicAdd(&d_cb0[j], ab);
     }
   }
 }
@@ -165,15 +193,12 @@ add_ln_fwd_kernel(const float* __restrict__ x_res, const T* __restrict__ y, cons
   const uint32_t seed32 = dropout_seed32(seed);
   const float inv_d = 1.f / static_cast<float>(d);
   const bool alias = static_cast<const void*>(out_T) == static_cast<const void*>(out_f32);
-  float gam[NCH][4], bet[NCH][4];
-#pragma unroll
-  for (int k = 0; k < NCH; ++k) {
-    const int c = 4 * (lane + 32 * k);
-    if (c < d) {
-      Vec4<float>::load(gamma + c, gam[k]);
-      Vec4<float>::load(beta + c, bet[k]);
-    }
+  extern __shared__ float ln_smem[];  // gamma | beta: keeps 2*d floats out of every thread's registers
+  for (int c = threadIdx.x; c < d; c += LN_THREADS) {
+    ln_smem[c] = gamma[c];
+    ln_smem[d + c] = beta[c];
   }
+  __syncthreads();
   for (int64_t row = warp0; row < M; row += nwarps) {
     float z[NCH][4];
     float sum = 0.f;
@@ -215,9 +240,11 @@ add_ln_fwd_kernel(const float* __restrict__ x_res, const T* __restrict__ y, cons
       const int c = 4 * (lane + 32 * k);
       if (c < d) {
         const int64_t idx = row * d + c;
-        float o[4];
+        float o[4], gm[4], bt[4];
+        Vec4<float>::load(ln_smem + c, gm);
+        Vec4<float>::load(ln_smem + d + c, bt);
 #pragma unroll
-        for (int e = 0; e < 4; ++e) o[e] = (z[k][e] - mean) * rstd * gam[k][e] + bet[k][e];
+        for (int e = 0; e < 4; ++e) o[e] = (z[k][e] - mean) * rstd * gm[e] + bt[e];
         if (zsave) Vec4<float>::store(zsave + idx, z[k]);
         Vec4<float>::store(out_f32 + idx, o);
         if (out_T != nullptr && !alias) Vec4<T>::store(out_T + idx, o);
@@ -226,35 +253,31 @@ add_ln_fwd_kernel(const float* __restrict__ x_res, const T* __restrict__ y, cons
   }
 }
 
-// LayerNorm backward.  Persistent warps walk the rows; every lane keeps the partial d_gamma / d_beta
-// (and, optionally, the column sums of the masked dy = bias gradient of the preceding Linear) of its
-// own columns in registers, the warps of a block combine through shared memory and flush one
-// atomicAdd per column per block.
+// LayerNorm backward.  Persistent warps walk the rows.  The column reductions (d_gamma, d_beta and,
+// optionally, the column sums of the masked dy = bias gradient of the preceding Linear) accumulate in a
+// private shared-memory strip per warp (plain read-modify-write, no atomics, no register arrays, which
+// keeps occupancy high enough to cover HBM latency); the strips are summed per block at the end and
+// flushed with one atomicAdd per column per block.
 template <typename T, int NCH>
 __global__ void __launch_bounds__(LN_THREADS)
 add_ln_bwd_kernel(const float* __restrict__ dout, const float* __restrict__ dout_add, const float* __restrict__ z,
                   const float* __restrict__ mean, const float* __restrict__ rstd, const float* __restrict__ gamma,
                   int M, int d, float p, uint64_t seed, float* __restrict__ dz_f32, T* __restrict__ dy_T,
                   float* __restrict__ d_gamma, float* __restrict__ d_beta, float* __restrict__ d_ybias) {
-  extern __shared__ float ln_smem[];  // [3][d]
-  const int lane = threadIdx.x & 31;
-  const int wpb = LN_THREADS / 32;
-  const int64_t warp0 = static_cast<int64_t>(blockIdx.x) * wpb + (threadIdx.x >> 5);
+  extern __shared__ float ln_smem[];  // gamma[d] | per warp: dg[d] db[d] dyb[d]
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  constexpr int wpb = LN_THREADS / 32;
+  const int64_t warp0 = static_cast<int64_t>(blockIdx.x) * wpb + warp;
   const int64_t nwarps = static_cast<int64_t>(gridDim.x) * wpb;
-  for (int c = threadIdx.x; c < 3 * d; c += LN_THREADS) ln_smem[c] = 0.f;
+  float* gam_s = ln_smem;
+  float* acc = ln_smem + d + warp * 3 * d;
+  for (int c = threadIdx.x; c < d; c += LN_THREADS) gam_s[c] = gamma[c];
+  for (int c = lane; c < 3 * d; c += 32) acc[c] = 0.f;
   __syncthreads();
   const float inv_keep = p > 0.f ? 1.f / (1.f - p) : 1.f;
   const uint32_t seed32 = dropout_seed32(seed);
   const float inv_d = 1.f / static_cast<float>(d);
   const bool alias = static_cast<const void*>(dy_T) == static_cast<const void*>(dz_f32);
-  float gam[NCH][4], dg[NCH][4], db[NCH][4], dyb[NCH][4];
-#pragma unroll
-  for (int k = 0; k < NCH; ++k) {
-    const int c = 4 * (lane + 32 * k);
-#pragma unroll
-    for (int e = 0; e < 4; ++e) dg[k][e] = db[k][e] = dyb[k][e] = gam[k][e] = 0.f;
-    if (c < d) Vec4<float>::load(gamma + c, gam[k]);
-  }
   for (int64_t row = warp0; row < M; row += nwarps) {
     const float mu = mean[row], rs = rstd[row];
     float dy[NCH][4], xh[NCH][4];
@@ -274,14 +297,28 @@ add_ln_bwd_kernel(const float* __restrict__ dout, const float* __restrict__ dout
           for (int e = 0; e < 4; ++e) dy[k][e] += t[e];
         }
 #pragma unroll
+        for (int e = 0; e < 4; ++e) xh[k][e] = (zv[e] - mu) * rs;
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < NCH; ++k) {
+      const int c = 4 * (lane + 32 * k);
+      if (c < d) {
+        float gm[4], ag[4], ab[4];
+        Vec4<float>::load(gam_s + c, gm);
+        Vec4<float>::load(acc + c, ag);
+        Vec4<float>::load(acc + d + c, ab);
+#pragma unroll
         for (int e = 0; e < 4; ++e) {
-          xh[k][e] = (zv[e] - mu) * rs;
-          const float g = dy[k][e] * gam[k][e];
+          const float g = dy[k][e] * gm[e];
           s1 += g;
           s2 += g * xh[k][e];
-          dg[k][e] += dy[k][e] * xh[k][e];
-          db[k][e] += dy[k][e];
+          ag[e] += dy[k][e] * xh[k][e];
+          ab[e] += dy[k][e];
+          dy[k][e] = g;  // from here on: dy * gamma
         }
+        Vec4<float>::store(acc + c, ag);
+        Vec4<float>::store(acc + d + c, ab);
       }
     }
     s1 = warp_sum(s1) * inv_d;
@@ -291,36 +328,29 @@ add_ln_bwd_kernel(const float* __restrict__ dout, const float* __restrict__ dout
       const int c = 4 * (lane + 32 * k);
       if (c < d) {
         const int64_t idx = row * d + c;
-        float dzv[4], dm[4], dyv[4];
+        float dzv[4], dm[4], dyv[4], ay[4];
         dropout_scale4(p, inv_keep, seed32, static_cast<uint64_t>(idx), dm);
+        Vec4<float>::load(acc + 2 * d + c, ay);
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
-          dzv[e] = rs * (dy[k][e] * gam[k][e] - s1 - xh[k][e] * s2);
+          dzv[e] = rs * (dy[k][e] - s1 - xh[k][e] * s2);
           dyv[e] = dzv[e] * dm[e];
-          dyb[k][e] += dyv[e];
+          ay[e] += dyv[e];
         }
+        Vec4<float>::store(acc + 2 * d + c, ay);
         if (dz_f32) Vec4<float>::store(dz_f32 + idx, dzv);
         if (dy_T != nullptr && !alias) Vec4<T>::store(dy_T + idx, dyv);
       }
     }
   }
-#pragma unroll
-  for (int k = 0; k < NCH; ++k) {
-    const int c = 4 * (lane + 32 * k);
-    if (c < d) {
-#pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        atomicAdd(&ln_smem[c + e], dg[k][e]);
-        atomicAdd(&ln_smem[d + c + e], db[k][e]);
-        atomicAdd(&ln_smem[2 * d + c + e], dyb[k][e]);
-      }
-    }
-  }
   __syncthreads();
-  for (int c = threadIdx.x; c < d; c += LN_THREADS) {
-    atomicAdd(&d_gamma[c], ln_smem[c]);
-    atomicAdd(&d_beta[c], ln_smem[d + c]);
-    if (d_ybias) atomicAdd(&d_ybias[c], ln_smem[2 * d + c]);
+  for (int c = threadIdx.x; c < 3 * d; c += LN_THREADS) {
+    float sum = 0.f;
+#pragma unroll
+    for (int w = 0; w < wpb; ++w) sum += ln_smem[d + w * 3 * d + c];
+    if (c < d) atomicAdd(&d_gamma[c], sum);
+    else if (c < 2 * d) atomicAdd(&d_beta[c - d], sum);
+    else if (d_ybias) atomicAdd(&d_ybias[c - 2 * d], sum);
   }
 }
 
@@ -431,8 +461,8 @@ static int ln_fwd_dispatch(int nch, int blocks, cudaStream_t st, const float* x_
                            const float* beta, float eps, int M, int d, float p, uint64_t seed, float* out_f32,
                            T* out_T, float* z, float* mean, float* rstd) {
 #define ME_LN_FWD(N)                                                                                        \
-  add_ln_fwd_kernel<T, N><<<blocks, LN_THREADS, 0, st>>>(x_res, y, gamma, beta, eps, M, d, p, seed, out_f32, \
-                                                         out_T, z, mean, rstd)
+  add_ln_fwd_kernel<T, N><<<blocks, LN_THREADS, 2 * d * sizeof(float), st>>>(x_res, y, gamma, beta, eps, M, d, p, \
+                                                                             seed, out_f32, out_T, z, mean, rstd)
   switch (nch) {
     case 1: ME_LN_FWD(1); break;
     case 2: ME_LN_FWD(2); break;
@@ -476,9 +506,16 @@ static int ln_bwd_dispatch(int nch, int blocks, size_t smem, cudaStream_t st, co
                            const float* dout_add, const float* z, const float* mean, const float* rstd,
                            const float* gamma, int M, int d, float p, uint64_t seed, float* dz_f32, T* dy_T,
                            float* d_gamma, float* d_beta, float* d_ybias) {
-#define ME_LN_BWD(N)                                                                                           \
-  add_ln_bwd_kernel<T, N><<<blocks, LN_THREADS, smem, st>>>(dout, dout_add, z, mean, rstd, gamma, M, d, p, seed, \
-                                                            dz_f32, dy_T, d_gamma, d_beta, d_ybias)
+#define ME_LN_BWD(N)                                                                                             \
+  do {                                                                                                           \
+    static bool configured = false;                                                                              \
+    if (!configured) {                                                                                           \
+      ME_CUDA(cudaFuncSetAttribute(add_ln_bwd_kernel<T, N>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); \
+      configured = true;                                                                                         \
+    }                                                                                                            \
+    add_ln_bwd_kernel<T, N><<<blocks, LN_THREADS, smem, st>>>(dout, dout_add, z, mean, rstd, gamma, M, d, p, seed, \
+                                                              dz_f32, dy_T, d_gamma, d_beta, d_ybias);            \
+  } while (0)
   switch (nch) {
     case 1: ME_LN_BWD(1); break;
     case 2: ME_LN_BWD(2); break;
@@ -498,9 +535,9 @@ int launch_add_ln_bwd(const float* dout, const float* dout_add, const float* z, 
   ME_CHECK(d % 4 == 0 && d <= 1024, "layernorm backward: d=%d must be a multiple of 4 and <= 1024", d);
   const int wpb = LN_THREADS / 32;
   int blocks = (M + wpb - 1) / wpb;
-  const int cap = sm_count() * 4;
+  const int cap = sm_count() * 2;
   if (blocks > cap) blocks = cap;
-  const size_t smem = 3 * static_cast<size_t>(d) * sizeof(float);
+  const size_t smem = (1 + 3 * (LN_THREADS / 32)) * static_cast<size_t>(d) * sizeof(float);
   if (dtype == ME_BF16)
     ln_bwd_dispatch<bf16>(ln_nch(d), blocks, smem, st, dout, dout_add, z, mean, rstd, gamma, M, d, p, seed, dz_f32,
                           static_cast<bf16*>(dy_T), d_gamma, d_beta, d_ybias);
@@ -559,8 +596,8 @@ extern "C" int me_embed_backward(const float* dx, const int64_t* tokens, const f
                                  float* d_emb, float* d_cw0, float* d_cb0, float* d_cw1, float* d_cb1,
                                  void* stream) {
   const int Ls = mode == ME_COND_CONTINUOUS_TOKEN ? L + 2 : L;
-  const int threads = d >= 512 ? 256 : 128;
-  embed_bwd_kernel<<<B * Ls, threads, 0, static_cast<cudaStream_t>(stream)>>>(
+  const int64_t rows = static_cast<int64_t>(B) * Ls;
+  embed_bwd_kernel<<<static_cast<int>((rows + EB_ROWS - 1) / EB_ROWS), EB_THREADS, 0, static_cast<cudaStream_t>(stream)>>>(
       dx, tokens, cond, B, L, d, d_cond, V, mode, pad_token, dropout_p, seed, d_emb, d_cw0, d_cb0, d_cw1, d_cb1);
   ME_LAUNCH_CHECK();
   return 0;

@@ -20,15 +20,12 @@ struct GemmParams {
 };
 
 
-// One chunk of CW accumulator columns of row m (already loaded from TMEM into r): bias / residual / ReLU /
-// ReLU-mask, then bf16 or fp32 stores (16-byte vectors when the row pitch allows) or split-K atomics.
-// addv / maskw were fetched by the caller while the TMEM load was in flight.
+// Epilogue arithmetic on one chunk of CW accumulator columns (already loaded from TMEM into r):
+// bias / residual / ReLU / ReLU-mask.  addv / maskw were fetched while the TMEM load was in flight.
 template <int CW>
-__device__ __forceinline__ void gemm_epilogue_chunk(const GemmParams& p, const uint32_t (&r)[CW], const float* bs,
-                                                    const float (&addv)[CW], const uint32_t (&maskw)[CW / 2],
-                                                    bool use_bias, bool do_add, bool do_mask, int m, int nb,
-                                                    bool full, bool vec_ok) {
-  float v[CW];
+__device__ __forceinline__ void gemm_epilogue_math(const GemmParams& p, const uint32_t (&r)[CW], const float* bs,
+                                                   const float (&addv)[CW], const uint32_t (&maskw)[CW / 2],
+                                                   bool use_bias, bool do_add, bool do_mask, float (&v)[CW]) {
 #pragma unroll
   for (int j = 0; j < CW; ++j) v[j] = __uint_as_float(r[j]);
   if (use_bias) {
@@ -51,6 +48,16 @@ __device__ __forceinline__ void gemm_epilogue_chunk(const GemmParams& p, const u
       if (!((w & 0x80000000u) == 0u && (w & 0x7FFF0000u) != 0u)) v[2 * j + 1] = 0.f;
     }
   }
+}
+
+// Direct stores of one chunk of row m: bf16 or fp32 (16-byte vectors when the row pitch allows) or split-K atomics.
+template <int CW>
+__device__ __forceinline__ void gemm_epilogue_chunk(const GemmParams& p, const uint32_t (&r)[CW], const float* bs,
+                                                    const float (&addv)[CW], const uint32_t (&maskw)[CW / 2],
+                                                    bool use_bias, bool do_add, bool do_mask, int m, int nb,
+                                                    bool full, bool vec_ok) {
+  float v[CW];
+  gemm_epilogue_math<CW>(p, r, bs, addv, maskw, use_bias, do_add, do_mask, v);
   if (p.splits > 1) {
     float* dp = static_cast<float*>(p.D) + static_cast<int64_t>(m) * p.ldd + nb;
 #pragma unroll

@@ -15,13 +15,15 @@
 namespace me {
 
 constexpr int G2_BM = 256, G2_BN = 256, G2_BK = 64;  // pair tile
-constexpr int G2_STAGES = 6;
+constexpr int G2_STAGES = 6;          // direct-store epilogue
+constexpr int G2_STAGES_STAGED = 4;   // staged epilogue: 64 KB of the ring become the output staging tile
+constexpr int G2_STG_BYTES = 128 * G2_BN * 2;  // bf16 [128 rows x 256 cols] as 4 SWIZZLE_128B blocks of 64 columns
 constexpr int G2_A_BYTES = 128 * G2_BK * 2;          // per CTA: its 128 rows of A
 constexpr int G2_B_BYTES = 128 * G2_BK * 2;          // per CTA: its half of the B tile
 constexpr int G2_STAGE_BYTES = G2_A_BYTES + G2_B_BYTES;
 constexpr int G2_EPI_THREADS = 256;
 constexpr int G2_THREADS = 64 + G2_EPI_THREADS;
-constexpr int G2_SMEM = G2_STAGES * G2_STAGE_BYTES + (2 * G2_STAGES + 4) * 8 + 16 + 2 * G2_BN * 4 + 1024;
+constexpr int G2_SMEM = G2_STAGES * G2_STAGE_BYTES + (2 * G2_STAGES + 5) * 8 + 16 + 2 * G2_BN * 4 + 1024;
 constexpr uint32_t G2_PEER_MASK = 0xFEFFFFFFu;       // clears the CTA-rank bit of a shared::cluster address
 
 __device__ __forceinline__ uint32_t cluster_ctarank() {
@@ -58,19 +60,25 @@ __device__ __forceinline__ void mbar_arrive_leader(uint64_t* bar) {
   asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(remote) : "memory");
 }
 
-template <bool A_MN, bool B_MN>
+// STAGED: bf16 output tile (and, for the ReLU-mask epilogue, the mask tile) goes through a swizzled
+// shared-memory tile and the TMA unit, so global traffic of the epilogue is fully coalesced.
+template <bool A_MN, bool B_MN, bool STAGED>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(G2_THREADS, 1)
-gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, GemmParams p) {
+gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                const __grid_constant__ CUtensorMap tmD, const __grid_constant__ CUtensorMap tmMask, GemmParams p) {
+  constexpr int G2_STAGES = STAGED ? me::G2_STAGES_STAGED : me::G2_STAGES;
   extern __shared__ uint8_t smem_raw2[];
   // identical carve-up in both CTAs (same offsets: the MMA and the multicast commit address both by offset)
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw2) + 1023) & ~uintptr_t(1023));
   uint8_t* smA = smem;
   uint8_t* smB = smem + G2_STAGES * G2_A_BYTES;
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + G2_STAGES * G2_STAGE_BYTES);
+  uint8_t* stg = smem + G2_STAGES * G2_STAGE_BYTES;  // STAGED only
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + G2_STAGES * G2_STAGE_BYTES + (STAGED ? G2_STG_BYTES : 0));
   uint64_t* empty_bar = full_bar + G2_STAGES;
   uint64_t* tfull_bar = empty_bar + G2_STAGES;   // [2]
   uint64_t* tempty_bar = tfull_bar + 2;          // [2] (used on the leader; both CTAs' epilogues arrive there)
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+  uint64_t* mask_bar = tempty_bar + 2;           // mask tile landed in the staging buffer (STAGED + mask)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(mask_bar + 1);
   float* bias_s = reinterpret_cast<float*>(tmem_slot + 4);  // [2][G2_BN]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -90,6 +98,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       mbar_init(&tfull_bar[s], 1);
       mbar_init(&tempty_bar[s], 2 * G2_EPI_THREADS);
     }
+    mbar_init(mask_bar, 1);
     fence_mbar_init();
   }
   if (warp == 1) {
@@ -194,11 +203,21 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       if (use_bias) {
         for (int c = et; c < G2_BN; c += G2_EPI_THREADS) bs[c] = (n0 + c < p.N) ? __ldg(p.bias + n0 + c) : 0.f;
       }
+      const bool mask_tile = STAGED && (p.flags & ME_EPI_RELU_MASK);
+      if (STAGED && et == 0) {
+        bulk_wait_read_all();  // the previous tile's TMA stores have finished reading the staging tile
+        if (mask_tile) {
+          mbar_arrive_expect_tx(mask_bar, G2_STG_BYTES);
+#pragma unroll
+          for (int blk = 0; blk < 4; ++blk) tma_load_2d(&tmMask, mask_bar, stg + blk * 16384, n0 + blk * 64, m0);
+        }
+      }
       named_bar_sync(1, G2_EPI_THREADS);
       const int m = m0 + row_in_tile;
       const bool row_ok = m < p.M;
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * G2_BN;
       mbar_wait(&tfull_bar[acc], acc_phase);
+      if (mask_tile) mbar_wait(mask_bar, it & 1);
       tc_fence_after();
 #pragma unroll 1
       for (int c0 = chalf * HALF; c0 < (chalf + 1) * HALF; c0 += CW) {
@@ -211,22 +230,61 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         uint32_t maskw[CW / 2];
         const bool do_add = (p.flags & ME_EPI_ADD_F32) && first_split && row_ok;
         const bool do_mask = (p.flags & ME_EPI_RELU_MASK) && row_ok;
-        gemm_epilogue_prefetch<CW>(p, addv, maskw, do_add, do_mask, m, nb, full);
-        tc_wait_ld();
-        if (row_ok) {
-          float bsl[CW];
+        if (STAGED) {
+          // this thread's 64 bytes inside the swizzled staging tile: block c0/64, row, four 16-byte chunks
+          uint8_t* srow = stg + (c0 >> 6) * 16384 + row_in_tile * 128;
+          const int q0 = (c0 & 63) >> 3;
+          if (mask_tile) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const uint4 u = *reinterpret_cast<const uint4*>(srow + (((q0 + j) ^ (row_in_tile & 7)) << 4));
+              maskw[4 * j] = u.x; maskw[4 * j + 1] = u.y; maskw[4 * j + 2] = u.z; maskw[4 * j + 3] = u.w;
+            }
+          }
+          tc_wait_ld();
+          float bsl[CW], v[CW];
           if (use_bias) {
 #pragma unroll
             for (int j = 0; j < CW; ++j) bsl[j] = bs[c0 + j];
           }
-          gemm_epilogue_chunk<CW>(p, r, bsl, addv, maskw, use_bias, do_add, do_mask, m, nb, full, vec_ok);
+          gemm_epilogue_math<CW>(p, r, bsl, addv, maskw, use_bias, false, mask_tile, v);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            uint4 u;
+            __nv_bfloat162* h2 = reinterpret_cast<__nv_bfloat162*>(&u);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) h2[e] = __floats2bfloat162_rn(v[8 * j + 2 * e], v[8 * j + 2 * e + 1]);
+            *reinterpret_cast<uint4*>(srow + (((q0 + j) ^ (row_in_tile & 7)) << 4)) = u;
+          }
+        } else {
+          gemm_epilogue_prefetch<CW>(p, addv, maskw, do_add, do_mask, m, nb, full);
+          tc_wait_ld();
+          if (row_ok) {
+            float bsl[CW];
+            if (use_bias) {
+#pragma unroll
+              for (int j = 0; j < CW; ++j) bsl[j] = bs[c0 + j];
+            }
+            gemm_epilogue_chunk<CW>(p, r, bsl, addv, maskw, use_bias, do_add, do_mask, m, nb, full, vec_ok);
+          }
         }
       }
       __syncwarp();
       tc_fence_before();
       if (leader) mbar_arrive(&tempty_bar[acc]);
       else mbar_arrive_leader(&tempty_bar[acc]);
+      if (STAGED) {
+        fence_proxy_async_smem();
+        named_bar_sync(1, G2_EPI_THREADS);  // the whole tile is in shared memory
+        if (et == 0) {
+#pragma unroll
+          for (int blk = 0; blk < 4; ++blk)
+            if (n0 + blk * 64 < p.N && m0 < p.M) tma_store_2d(&tmD, stg + blk * 16384, n0 + blk * 64, m0);
+          bulk_commit();
+        }
+      }
     }
+    if (STAGED && et == 0) bulk_wait_all();
   }
 
   tc_fence_before();
@@ -237,18 +295,21 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   }
 }
 
-template <bool A_MN, bool B_MN>
-static int launch_pair(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p, int grid, cudaStream_t st) {
-  auto kern = gemm_tc2_kernel<A_MN, B_MN>;
+template <bool A_MN, bool B_MN, bool STAGED>
+static int launch_pair(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmD, const CUtensorMap& tmMask,
+                       const GemmParams& p, int grid, cudaStream_t st) {
+  auto kern = gemm_tc2_kernel<A_MN, B_MN, STAGED>;
   static bool configured = false;
   if (!configured) {
     ME_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, G2_SMEM));
     configured = true;
   }
-  kern<<<grid, G2_THREADS, G2_SMEM, st>>>(tmA, tmB, p);
+  kern<<<grid, G2_THREADS, G2_SMEM, st>>>(tmA, tmB, tmD, tmMask, p);
   ME_LAUNCH_CHECK();
   return 0;
 }
+
+int g_pair_force_direct = 0;  // test hook: 1 = never use the staged epilogue
 
 // Returns 0 on success, 1 on error, -1 when the shape is better served by the 1-CTA kernel.
 int launch_gemm_bf16_pair(const void* A, const void* B, void* D, int M, int N, int K, int lda, int ldb, int ldd,
@@ -290,11 +351,25 @@ int launch_gemm_bf16_pair(const void* A, const void* B, void* D, int M, int N, i
   if (splits > 1) ME_CUDA(cudaMemsetAsync(D, 0, static_cast<size_t>(M) * ldd * sizeof(float), st));
   const int total = tiles * splits;
   const int grid = 2 * (total < pairs ? total : pairs);
+  // staged (TMA-store) epilogue: bf16 output without residual add / split-K and with 16-byte aligned rows
+  bool staged = !a_mn && out_dtype == ME_BF16 && splits == 1 && ldd % 8 == 0 && !(flags & ME_EPI_ADD_F32) &&
+                (reinterpret_cast<uintptr_t>(D) & 15) == 0;
+  if ((flags & ME_EPI_RELU_MASK) && (ldmask % 8 != 0 || (reinterpret_cast<uintptr_t>(relu_mask) & 15) != 0)) staged = false;
+  if (g_pair_force_direct) staged = false;
+  CUtensorMap tmD = tmA, tmMask = tmA;  // placeholders when unused
+  if (staged) {
+    if (make_tmap_2d_bf16(&tmD, D, N, M, ldd, 64, 128)) return 1;
+    if (flags & ME_EPI_RELU_MASK) {
+      if (make_tmap_2d_bf16(&tmMask, relu_mask, N, M, ldmask, 64, 128)) return 1;
+    }
+  }
   cudaEvent_t pe = prof_begin(2.0 * M * N * K, st);
   int rc;
-  if (!a_mn && !b_mn) rc = launch_pair<false, false>(tmA, tmB, p, grid, st);
-  else if (!a_mn && b_mn) rc = launch_pair<false, true>(tmA, tmB, p, grid, st);
-  else rc = launch_pair<true, true>(tmA, tmB, p, grid, st);
+  if (!a_mn && !b_mn) rc = staged ? launch_pair<false, false, true>(tmA, tmB, tmD, tmMask, p, grid, st)
+                                  : launch_pair<false, false, false>(tmA, tmB, tmD, tmMask, p, grid, st);
+  else if (!a_mn && b_mn) rc = staged ? launch_pair<false, true, true>(tmA, tmB, tmD, tmMask, p, grid, st)
+                                      : launch_pair<false, true, false>(tmA, tmB, tmD, tmMask, p, grid, st);
+  else rc = launch_pair<true, true, false>(tmA, tmB, tmD, tmMask, p, grid, st);
   prof_end(pe, st);
   return rc;
 }

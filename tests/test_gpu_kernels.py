@@ -456,3 +456,18 @@ def test_gemm_tcgen05_cta_pair_epilogues(flags):
     got = gemm_bf16(As, Bs, M, N, K, 0, 0, ME_BF16, flags=f, tile_n=512, **kw)
     torch.cuda.synchronize()
     assert rel_err(got.float(), want) < 3e-3
+
+
+@pytest.mark.parametrize("M,N,K,b_mn", [(300, 1007, 128, 0), (1000, 520, 192, 1), (256, 256, 64, 0)])
+def test_gemm_tcgen05_cta_pair_staged_store_ragged(M, N, K, b_mn):
+    """bf16 output through the shared-memory staging tile + TMA store, ragged M / N, padded row pitch."""
+    A, B, As, Bs = _operands(M, N, K, 0, b_mn, seed=17)
+    bias = torch.randn(N, device="cuda")
+    ldd = (N + 7) // 8 * 8
+    want = (A.float() @ B.float().t() + bias)
+    got = gemm_bf16(As, Bs, M, N, K, 0, b_mn, ME_BF16, flags=_lib.EPI_BIAS, bias=bias, tile_n=512, ldd=ldd)
+    torch.cuda.synchronize()
+    assert rel_err(got[:, :N].float(), want) < 3e-3
+    if ldd != N:
+        pad = got[:, N:].float()                          # pad columns: untouched (NaN fill) or written as zero
+        assert (torch.isnan(pad) | (pad == 0)).all()
