@@ -26,6 +26,8 @@ constexpr int FB_EROWS = 192;
 constexpr int FB_COMPUTE_THREADS = 256;  // 8 warps: warp w and w+4 share TMEM lanes 32*(w&3).. and split the key columns
 constexpr int FB_CONTROL_WARP = 8;       // one more warp: TMA producer + MMA issuer, TMEM alloc
 constexpr int FB_THREADS = FB_COMPUTE_THREADS + 32;
+constexpr int FB_DE_COPIES = 32;      // private dE accumulators: concurrently running CTAs walk the same bands of E
+                                      // in lockstep, and same-address reduce-adds serialise in the L2 slices
 constexpr int FB_STG_MAX = 272;       // staging row pitch for dh = 64: (dh + 4) floats
 constexpr int FB_OFF_K = 0;
 constexpr int FB_OFF_V = FB_OFF_K + 8192;
@@ -52,7 +54,7 @@ struct FbParams {
   const float* lse;
   const float* dsum;
   float* dq_ws;  // fp32 [B, H, L, dh + 4]: dq accumulated across key tiles (rows padded like the staging rows)
-  float* dE_ws;  // fp32 [max_seq, dh + 4]
+  float* dE_ws;  // fp32 [FB_DE_COPIES, max_seq, dh + 4]
   bf16* dk;
   bf16* dv;
   float scale_log2, scale;
@@ -112,6 +114,10 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   const int nq = (p.L + FB_BM - 1) / FB_BM;
   const int qi0 = j0 / FB_BM;
   const int nsteps = nq - qi0;
+  // consecutive block ids (the CTAs resident at the same time) accumulate dE into different copies
+  float* const dE_mine =
+      p.dE_ws + static_cast<int64_t>((blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z)) % FB_DE_COPIES) *
+                    p.max_seq * (DH + 4);
 
   if (tid == 0) {
     if ((smem_u32(fb_smem) & 1023u) != 0) __trap();
@@ -355,11 +361,11 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
                                 stg0 + r0 * STG, n * STG);
         } else {
           const int n = min(32, p.max_seq - (e0 + r0));
-          if (n > 0) bulk_reduce_add_f32(p.dE_ws + static_cast<int64_t>(e0 + r0) * (DH + 4), stg1 + r0 * STG, n * STG);
+          if (n > 0) bulk_reduce_add_f32(dE_mine + static_cast<int64_t>(e0 + r0) * (DH + 4), stg1 + r0 * STG, n * STG);
           if (quarter < 2) {
             const int n2 = min(32, p.max_seq - (e0 + 128 + r0));
             if (n2 > 0)
-              bulk_reduce_add_f32(p.dE_ws + static_cast<int64_t>(e0 + 128 + r0) * (DH + 4), stg2 + r0 * STG, n2 * STG);
+              bulk_reduce_add_f32(dE_mine + static_cast<int64_t>(e0 + 128 + r0) * (DH + 4), stg2 + r0 * STG, n2 * STG);
           }
         }
         bulk_commit();
@@ -431,7 +437,7 @@ __global__ void attn_bwd_prep_kernel(const bf16* __restrict__ out, const bf16* _
   dsum[(static_cast<int64_t>(b) * H + h) * L + i] = acc;
 }
 
-// dq (bf16, strided) = dq_ws (fp32 [B, H, L, dh + 4]);  dE[e, :] += dE_ws[e, :] (rows padded likewise)
+// dq (bf16, strided) = dq_ws (fp32 [B, H, L, dh + 4]);  dE[e, :] += sum over copies of dE_ws[., e, :] (rows padded likewise)
 __global__ void attn_bwd_finish_kernel(const float* __restrict__ dq_ws, bf16* __restrict__ dq, int64_t q_sb,
                                        int64_t q_si, int64_t q_sh, int B, int H, int L, int dh,
                                        const float* __restrict__ dE_ws, float* __restrict__ dE, int max_seq) {
@@ -457,9 +463,12 @@ __global__ void attn_bwd_finish_kernel(const float* __restrict__ dq_ws, bf16* __
       const int64_t u = t - n_dq;
       const int c = static_cast<int>(u % q4) * 4;
       const int64_t e = u / q4;
-      const float4 v = *reinterpret_cast<const float4*>(dE_ws + e * (dh + 4) + c);
       float4 o = *reinterpret_cast<float4*>(dE + e * dh + c);
-      o.x += v.x; o.y += v.y; o.z += v.z; o.w += v.w;
+      for (int cp = 0; cp < FB_DE_COPIES; ++cp) {
+        const float4 v =
+            *reinterpret_cast<const float4*>(dE_ws + (static_cast<int64_t>(cp) * max_seq + e) * (dh + 4) + c);
+        o.x += v.x; o.y += v.y; o.z += v.z; o.w += v.w;
+      }
       *reinterpret_cast<float4*>(dE + e * dh + c) = o;
     }
   }
@@ -545,5 +554,5 @@ int launch_attn_bwd_tc(const me_attn_bwd_args* ba) {
 }  // namespace me
 
 extern "C" int64_t me_attention_backward_workspace_floats(int B, int H, int L, int dh, int max_seq) {
-  return (static_cast<int64_t>(B) * H * L + max_seq) * (dh + 4);
+  return (static_cast<int64_t>(B) * H * L + static_cast<int64_t>(me::FB_DE_COPIES) * max_seq) * (dh + 4);
 }
