@@ -171,6 +171,9 @@ typedef struct me_attn_bwd_args {
 } me_attn_bwd_args;
 int me_attention_backward(const me_attn_bwd_args* a);
 int64_t me_attention_backward_workspace_floats(int B, int H, int L, int dh, int max_seq);
+/* Debugging hook (kernel tuning only): when device_buf is non-NULL (>= 3*16*16 int64), one CTA of the
+ * tensor-core attention backward kernel records clock64() stamps of its phases there; NULL disables. */
+int me_debug_trace_set(long long* device_buf);
 
 /* ---------------------------------------------------------------------------------------
  * One encoder layer (music_multi.py:126-135): attention block + FFN block, post-LN.

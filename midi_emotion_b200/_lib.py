@@ -71,6 +71,7 @@ _PROTOS = {
     "me_device_is_sm100": (C.c_int, []),
     "me_profile_enable": (C.c_int, [C.c_int]),
     "me_profile_collect": (C.c_int, [C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_int)]),
+    "me_debug_trace_set": (C.c_int, [_vp]),
     "me_sizeof_attn_args": (C.c_int, []),
     "me_sizeof_attn_bwd_args": (C.c_int, []),
     "me_sizeof_layer_args": (C.c_int, []),

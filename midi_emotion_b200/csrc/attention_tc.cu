@@ -126,21 +126,25 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     const uint32_t ph = (t >> 1) & 1;
     const uint32_t k_addr = smem_u32(sStage + s * FA_STAGE_BYTES);
     const uint32_t v_addr = k_addr + FA_K_BYTES, e_addr = k_addr + 2 * FA_K_BYTES;
-    if (tid == 0) {
+    // Warp 0 issues converged with one elected lane: from a divergent `if (tid == 0)` the compiler wraps
+    // every tcgen05.mma in a serialising loop (~90 cycles per instruction).
+    if (warp == 0) {
       if (t == 0) mbar_wait(q_full, 0);
       mbar_wait(&kv_full[s], ph);
       tc_fence_after();
+      if (elect_one()) {
 #pragma unroll
-      for (int k = 0; k < DH / 16; ++k)
-        umma_bf16(tmem_base + FA_COL_S, make_smem_desc_sw128(q_addr + k * 32, 16, 1024),
-                  make_smem_desc_sw128(k_addr + k * 32, 16, 1024), idesc_s, k > 0);
+        for (int k = 0; k < DH / 16; ++k)
+          umma_bf16(tmem_base + FA_COL_S, make_smem_desc_sw128(q_addr + k * 32, 16, 1024),
+                    make_smem_desc_sw128(k_addr + k * 32, 16, 1024), idesc_s, k > 0);
 #pragma unroll
-      for (int k = 0; k < DH / 16; ++k)
-        umma_bf16(tmem_base + FA_COL_R, make_smem_desc_sw128(q_addr + k * 32, 16, 1024),
-                  make_smem_desc_sw128(e_addr + k * 32, 16, 1024), idesc_r, k > 0);
-      umma_commit(s_full);
+        for (int k = 0; k < DH / 16; ++k)
+          umma_bf16(tmem_base + FA_COL_R, make_smem_desc_sw128(q_addr + k * 32, 16, 1024),
+                    make_smem_desc_sw128(e_addr + k * 32, 16, 1024), idesc_r, k > 0);
+        umma_commit(s_full);
+      }
+      __syncwarp();
     }
-    __syncwarp();
 
     const int j0 = t * FA_BN;
     uint32_t kp0 = 0, kp1 = 0;
@@ -215,16 +219,18 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     fence_proxy_async_smem();  // generic-proxy writes of P -> visible to the tensor core (async proxy)
     tc_fence_before();
     __syncthreads();           // P complete, S/R consumed by every row
-    if (tid == 0) {
+    if (warp == 0) {
       tc_fence_after();
+      if (elect_one()) {
 #pragma unroll
-      for (int k = 0; k < FA_BN / 16; ++k)
-        umma_bf16(tmem_base + FA_COL_S, make_smem_desc_sw128(p_addr + k * 32, 16, 1024),
-                  make_smem_desc_sw128(v_addr + k * 2048, 8192, 1024), idesc_o, k > 0);
-      umma_commit(o_full);
-      umma_commit(&kv_free[s]);
+        for (int k = 0; k < FA_BN / 16; ++k)
+          umma_bf16(tmem_base + FA_COL_S, make_smem_desc_sw128(p_addr + k * 32, 16, 1024),
+                    make_smem_desc_sw128(v_addr + k * 2048, 8192, 1024), idesc_o, k > 0);
+        umma_commit(o_full);
+        umma_commit(&kv_free[s]);
+      }
+      __syncwarp();
     }
-    __syncwarp();
     mbar_wait(o_full, t & 1);
     tc_fence_after();
 #pragma unroll
@@ -236,9 +242,10 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       for (int c = 0; c < 16; ++c) O[c0 + c] = fmaf(O[c0 + c], alpha, __uint_as_float(ov[c]));
     }
     tc_fence_before();
-    if (tid == 0 && t + 2 < nt) {
+    if (warp == 0 && t + 2 < nt) {
       mbar_wait(&kv_free[s], ph);
-      load_tile(t + 2);
+      if (elect_one()) load_tile(t + 2);
+      __syncwarp();
     }
     __syncthreads();           // P.V tile read out of TMEM by every row before the next S/R MMAs
   }

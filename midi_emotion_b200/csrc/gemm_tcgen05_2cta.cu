@@ -115,7 +115,9 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
 
   const int total_tiles = p.num_m_tiles * p.num_n_tiles * p.splits;  // in units of 256 x 256 pair tiles
 
-  if (threadIdx.x == 0) {
+  // Producer and issuer warps run their loops converged and one elected lane issues: from a divergent
+  // single-thread branch the compiler wraps every TMA / tcgen05.mma instruction in a serialising loop.
+  if (warp == 0) {
     // ============================== TMA producer (both CTAs) ==============================
     int s = 0;
     uint32_t phase = 0;
@@ -128,27 +130,30 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       const int kb1 = min(p.num_kb, kb0 + p.kb_per_split);
       for (int kb = kb0; kb < kb1; ++kb) {
         mbar_wait(&empty_bar[s], phase ^ 1);
-        if (leader) mbar_arrive_expect_tx(&full_bar[s], 2 * G2_STAGE_BYTES);
-        uint8_t* a_dst = smA + s * G2_A_BYTES;
-        uint8_t* b_dst = smB + s * G2_B_BYTES;
-        if (!A_MN) {
-          tma_load_2d_pair(&tmA, &full_bar[s], a_dst, kb * G2_BK, m0);
-        } else {
+        if (elect_one()) {
+          if (leader) mbar_arrive_expect_tx(&full_bar[s], 2 * G2_STAGE_BYTES);
+          uint8_t* a_dst = smA + s * G2_A_BYTES;
+          uint8_t* b_dst = smB + s * G2_B_BYTES;
+          if (!A_MN) {
+            tma_load_2d_pair(&tmA, &full_bar[s], a_dst, kb * G2_BK, m0);
+          } else {
 #pragma unroll
-          for (int blk = 0; blk < 2; ++blk)
-            tma_load_2d_pair(&tmA, &full_bar[s], a_dst + blk * (G2_BK * 128), m0 + blk * 64, kb * G2_BK);
-        }
-        if (!B_MN) {
-          tma_load_2d_pair(&tmB, &full_bar[s], b_dst, kb * G2_BK, n0);
-        } else {
+            for (int blk = 0; blk < 2; ++blk)
+              tma_load_2d_pair(&tmA, &full_bar[s], a_dst + blk * (G2_BK * 128), m0 + blk * 64, kb * G2_BK);
+          }
+          if (!B_MN) {
+            tma_load_2d_pair(&tmB, &full_bar[s], b_dst, kb * G2_BK, n0);
+          } else {
 #pragma unroll
-          for (int blk = 0; blk < 2; ++blk)
-            tma_load_2d_pair(&tmB, &full_bar[s], b_dst + blk * (G2_BK * 128), n0 + blk * 64, kb * G2_BK);
+            for (int blk = 0; blk < 2; ++blk)
+              tma_load_2d_pair(&tmB, &full_bar[s], b_dst + blk * (G2_BK * 128), n0 + blk * 64, kb * G2_BK);
+          }
         }
+        __syncwarp();
         if (++s == G2_STAGES) { s = 0; phase ^= 1; }
       }
     }
-  } else if (threadIdx.x == 32 && leader) {
+  } else if (warp == 1 && leader) {
     // ============================== MMA issuer (leader CTA) ==============================
     constexpr uint32_t idesc = make_idesc_bf16(G2_BM, G2_BN, A_MN ? 1 : 0, B_MN ? 1 : 0);
     int s = 0;
@@ -168,16 +173,19 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         tc_fence_after();
         const uint32_t a_addr = smem_u32(smA + s * G2_A_BYTES);
         const uint32_t b_addr = smem_u32(smB + s * G2_B_BYTES);
+        if (elect_one()) {
 #pragma unroll
-        for (int k = 0; k < G2_BK / 16; ++k) {
-          const uint64_t ad = A_MN ? make_smem_desc_sw128(a_addr + k * 2048, G2_BK * 128, 1024)
-                                   : make_smem_desc_sw128(a_addr + k * 32, 16, 1024);
-          const uint64_t bd = B_MN ? make_smem_desc_sw128(b_addr + k * 2048, G2_BK * 128, 1024)
-                                   : make_smem_desc_sw128(b_addr + k * 32, 16, 1024);
-          umma_bf16_pair(d_tmem, ad, bd, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+          for (int k = 0; k < G2_BK / 16; ++k) {
+            const uint64_t ad = A_MN ? make_smem_desc_sw128(a_addr + k * 2048, G2_BK * 128, 1024)
+                                     : make_smem_desc_sw128(a_addr + k * 32, 16, 1024);
+            const uint64_t bd = B_MN ? make_smem_desc_sw128(b_addr + k * 2048, G2_BK * 128, 1024)
+                                     : make_smem_desc_sw128(b_addr + k * 32, 16, 1024);
+            umma_bf16_pair(d_tmem, ad, bd, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+          }
+          umma_commit_pair(&empty_bar[s]);                      // frees the stage in both CTAs
+          if (kb == kb1 - 1) umma_commit_pair(&tfull_bar[acc]);  // accumulators complete in both CTAs
         }
-        umma_commit_pair(&empty_bar[s]);                      // frees the stage in both CTAs
-        if (kb == kb1 - 1) umma_commit_pair(&tfull_bar[acc]);  // accumulators complete in both CTAs
+        __syncwarp();
         if (++s == G2_STAGES) { s = 0; phase ^= 1; }
       }
     }

@@ -59,3 +59,20 @@ t_f = timeit(lambda: _lib.call("me_attention_forward", C.byref(a)))
 t_b = timeit(lambda: _lib.call("me_attention_backward", C.byref(ba)))
 print(f"attention B={B} H={H} L={L} dh={dh}: fwd {t_f * 1e3:.1f} us ({fwd_flops / t_f / 1e9:.1f} TFLOP/s useful), "
       f"bwd {t_b * 1e3:.1f} us ({2.5 * fwd_flops / t_b / 1e9:.1f} TFLOP/s useful, incl. prep/convert)")
+
+if os.environ.get("TRACE"):
+    # per-phase clock stamps of one CTA of the backward kernel (me_debug_trace_set)
+    buf = torch.zeros(3 * 16 * 16, dtype=torch.int64, device="cuda")
+    _lib.call("me_debug_trace_set", buf.data_ptr())
+    _lib.call("me_attention_backward", C.byref(ba))
+    torch.cuda.synchronize()
+    _lib.call("me_debug_trace_set", None)
+    t = buf.cpu().view(3, 16, 16)
+    t0 = int(t[t > 0].min())
+    names = {0: "warp0", 1: "warp7", 2: "ctrl"}
+    for role in range(3):
+        for st in range(16):
+            row = t[role, st]
+            if int(row.max()) == 0:
+                continue
+            print(names[role], "step", st, " ".join(f"{(int(v) - t0) if v > 0 else -1:7d}" for v in row[:15]))
