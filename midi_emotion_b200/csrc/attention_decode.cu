@@ -88,23 +88,35 @@ attn_decode_kernel(const bf16* __restrict__ q, const bf16* __restrict__ k, const
 #pragma unroll
   for (int c = 0; c < ND; ++c) o[c] = 0.f;
 
-  for (int j0 = warp * 8; j0 <= t; j0 += AD_WARPS * 8) {
-    const int j = j0 + kslot;
-    const bool valid = j <= t && !(kp && kp[j]);
+  // Software pipeline: the loads of the next 8 keys are in flight while the current ones are folded in.
+  // Rows of pad keys are loaded like any other (the key-pad byte arrives with them) and skipped afterwards,
+  // so no load waits on another one.
+  struct Tile {
     uint4 kr[NC], er[NC], vr[NC];
+    uint32_t pad;
+  };
+  auto fetch = [&](int j0, Tile& tl) {
+    const int j = j0 + kslot;
 #pragma unroll
-    for (int c = 0; c < NC; ++c) {
-      kr[c] = er[c] = vr[c] = make_uint4(0, 0, 0, 0);
-      if (valid && live[c]) {
-        kr[c] = __ldg(reinterpret_cast<const uint4*>(kb + j * p.k_sj) + g + 4 * c);
-        er[c] = __ldg(reinterpret_cast<const uint4*>(Eb + static_cast<int64_t>(j) * DH) + g + 4 * c);
-        vr[c] = __ldg(reinterpret_cast<const uint4*>(vb + j * p.v_sj) + g + 4 * c);
+    for (int c = 0; c < NC; ++c) tl.kr[c] = tl.er[c] = tl.vr[c] = make_uint4(0, 0, 0, 0);
+    tl.pad = 1u;
+    if (j <= t) {
+#pragma unroll
+      for (int c = 0; c < NC; ++c) {
+        if (live[c]) {
+          tl.kr[c] = __ldg(reinterpret_cast<const uint4*>(kb + j * p.k_sj) + g + 4 * c);
+          tl.er[c] = __ldg(reinterpret_cast<const uint4*>(Eb + static_cast<int64_t>(j) * DH) + g + 4 * c);
+          tl.vr[c] = __ldg(reinterpret_cast<const uint4*>(vb + j * p.v_sj) + g + 4 * c);
+        }
       }
+      tl.pad = kp ? static_cast<uint32_t>(__ldg(kp + j)) : 0u;
     }
-    float x = dot_chunks<NC>(qf, kr) + dot_chunks<NC>(qf, er);
+  };
+  auto fold = [&](const Tile& tl) {
+    float x = dot_chunks<NC>(qf, tl.kr) + dot_chunks<NC>(qf, tl.er);
     x += __shfl_xor_sync(0xffffffffu, x, 1);
     x += __shfl_xor_sync(0xffffffffu, x, 2);
-    if (valid) {
+    if (tl.pad == 0u) {
       if (x > m) {  // rescale the running state (rare once the maximum has settled)
         const float a = fast_exp2(m - x);
         l *= a;
@@ -116,13 +128,26 @@ attn_decode_kernel(const bf16* __restrict__ q, const bf16* __restrict__ k, const
       l += pj;
 #pragma unroll
       for (int c = 0; c < NC; ++c) {
-        const uint32_t w[4] = {vr[c].x, vr[c].y, vr[c].z, vr[c].w};
+        const uint32_t w[4] = {tl.vr[c].x, tl.vr[c].y, tl.vr[c].z, tl.vr[c].w};
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
           o[c * 8 + 2 * e] = fmaf(pj, bf_lo(w[e]), o[c * 8 + 2 * e]);
           o[c * 8 + 2 * e + 1] = fmaf(pj, bf_hi(w[e]), o[c * 8 + 2 * e + 1]);
         }
       }
+    }
+  };
+  {
+    constexpr int STEP = AD_WARPS * 8;
+    Tile ta, tb;
+    int j0 = warp * 8;
+    if (j0 <= t) fetch(j0, ta);
+    for (; j0 <= t; j0 += 2 * STEP) {   // warp-uniform trip count
+      const bool more = j0 + STEP <= t;
+      if (more) fetch(j0 + STEP, tb);
+      fold(ta);
+      if (j0 + 2 * STEP <= t) fetch(j0 + 2 * STEP, ta);
+      if (more) fold(tb);
     }
   }
 

@@ -8,7 +8,8 @@
 //
 //   * Q, K, V and the needed band of E are brought in by TMA (4-D maps over the strided q/k/v views,
 //     SWIZZLE_128B; rows past the sequence / past max_seq are zero-filled by the TMA unit);
-//   * tcgen05.mma (M=128): S = Q K^T (N=64) and the relative band R = Q Eband^T (N=192), where Eband is
+//   * tcgen05.mma (M=128): [S | R] = Q [K ; Eband]^T (N=256, K and the band of E back to back in shared
+//     memory), i.e. S = Q K^T (N=64) and the relative band R = Q Eband^T (N=192), where Eband is
 //     the 191 consecutive rows of E a 128x64 tile can touch: R[a, c] = q_a . E[e0 + c],
 //     e0 = max_seq - 128 - (i0 - j0).  The skew of the reference (pad/reshape/slice,
 //     music_multi.py:245-262) is the identity  Srel[a, b] = R[a, 127 - a + b]: thread a (TMEM lane a)
@@ -49,7 +50,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
                    const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmE, FaParams p) {
   extern __shared__ __align__(1024) uint8_t fa_smem[];
   uint8_t* sQ = fa_smem;
-  uint8_t* sStage = sQ + FA_Q_BYTES;  // per stage: K | V | E
+  uint8_t* sStage = sQ + FA_Q_BYTES;  // per stage: K | E | V  ([K ; Eband] is one 256-row B operand)
   uint8_t* sP = sStage + 2 * FA_STAGE_BYTES;
   uint64_t* bars = reinterpret_cast<uint64_t*>(sP + FA_P_BYTES);
   uint64_t* q_full = bars + 0;
@@ -73,8 +74,8 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     uint8_t* st = sStage + s * FA_STAGE_BYTES;
     mbar_arrive_expect_tx(&kv_full[s], FA_STAGE_BYTES);
     tma_load_4d(&tmK, &kv_full[s], st, 0, h, j0, b);
-    tma_load_4d(&tmV, &kv_full[s], st + FA_K_BYTES, 0, h, j0, b);
-    tma_load_2d(&tmE, &kv_full[s], st + 2 * FA_K_BYTES, 0, p.max_seq - FA_BM - (i0 - j0));
+    tma_load_2d(&tmE, &kv_full[s], st + FA_K_BYTES, 0, p.max_seq - FA_BM - (i0 - j0));
+    tma_load_4d(&tmV, &kv_full[s], st + FA_K_BYTES + FA_E_BYTES, 0, h, j0, b);
   };
 
   if (tid == 0) {
@@ -105,8 +106,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  constexpr uint32_t idesc_s = make_idesc_bf16(FA_BM, FA_BN, 0, 0);
-  constexpr uint32_t idesc_r = make_idesc_bf16(FA_BM, FA_EROWS, 0, 0);
+  constexpr uint32_t idesc_sr = make_idesc_bf16(FA_BM, FA_BN + FA_EROWS, 0, 0);
   constexpr uint32_t idesc_o = make_idesc_bf16(FA_BM, DH, 0, 1);
   const uint32_t q_addr = smem_u32(sQ), p_addr = smem_u32(sP);
 
@@ -125,7 +125,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     const int s = t & 1;
     const uint32_t ph = (t >> 1) & 1;
     const uint32_t k_addr = smem_u32(sStage + s * FA_STAGE_BYTES);
-    const uint32_t v_addr = k_addr + FA_K_BYTES, e_addr = k_addr + 2 * FA_K_BYTES;
+    const uint32_t v_addr = k_addr + FA_K_BYTES + FA_E_BYTES;
     // Warp 0 issues converged with one elected lane: from a divergent `if (tid == 0)` the compiler wraps
     // every tcgen05.mma in a serialising loop (~90 cycles per instruction).
     if (warp == 0) {
@@ -134,13 +134,9 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       tc_fence_after();
       if (elect_one()) {
 #pragma unroll
-        for (int k = 0; k < DH / 16; ++k)
+        for (int k = 0; k < DH / 16; ++k)  // [S | R] = Q [K ; Eband]^T, one N = 256 instruction per 16 head dims
           umma_bf16(tmem_base + FA_COL_S, make_smem_desc_sw128(q_addr + k * 32, 16, 1024),
-                    make_smem_desc_sw128(k_addr + k * 32, 16, 1024), idesc_s, k > 0);
-#pragma unroll
-        for (int k = 0; k < DH / 16; ++k)
-          umma_bf16(tmem_base + FA_COL_R, make_smem_desc_sw128(q_addr + k * 32, 16, 1024),
-                    make_smem_desc_sw128(e_addr + k * 32, 16, 1024), idesc_r, k > 0);
+                    make_smem_desc_sw128(k_addr + k * 32, 16, 1024), idesc_sr, k > 0);
         umma_commit(s_full);
       }
       __syncwarp();
