@@ -93,6 +93,47 @@ __device__ __forceinline__ void gemm_epilogue_chunk(const GemmParams& p, const u
   }
 }
 
+// fp32 output of one 32-column chunk with full-sector global traffic.  The accumulator layout is one row
+// per lane; stored that way a warp-wide 16-byte store touches 32 rows (half a sector each), and so does the
+// residual load.  Here the chunk is transposed through a 2 KB per-warp scratch tile, 16 columns at a time:
+// afterwards lane l of store k holds row 8k + l/4, columns 4*(l%4).. of the half, i.e. every instruction
+// moves eight 64-byte row segments; the fp32 residual is fetched in the same layout and added there.
+// v: bias / ReLU / mask already applied.  m_warp: global row of lane 0.  Converged warp required.
+__device__ __forceinline__ void gemm_addend_coalesced(const GemmParams& p, bool do_add, int m_warp, int nb, int lane,
+                                                      float4 (&a)[8]) {  // issued before the TMEM wait
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int r = 8 * (i & 3) + (lane >> 2), m = m_warp + r;
+    a[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (do_add && m < p.M)
+      a[i] = __ldg(reinterpret_cast<const float4*>(p.addend + static_cast<int64_t>(m) * p.ldd + nb + 16 * (i >> 2) +
+                                                   4 * (lane & 3)));
+  }
+}
+__device__ __forceinline__ void gemm_store_f32_coalesced(const GemmParams& p, const float (&v)[32], const float4 (&a)[8],
+                                                         int m_warp, int nb, uint8_t* scratch, int lane) {
+  const int my_key = (lane >> 1) & 3;
+#pragma unroll
+  for (int hlf = 0; hlf < 2; ++hlf) {
+    __syncwarp();  // the previous round's reads are done
+#pragma unroll
+    for (int c = 0; c < 4; ++c)
+      *reinterpret_cast<float4*>(scratch + lane * 64 + ((c ^ my_key) << 4)) =
+          make_float4(v[16 * hlf + 4 * c], v[16 * hlf + 4 * c + 1], v[16 * hlf + 4 * c + 2], v[16 * hlf + 4 * c + 3]);
+    __syncwarp();
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int r = 8 * k + (lane >> 2), c = lane & 3;
+      float4 t = *reinterpret_cast<const float4*>(scratch + r * 64 + ((c ^ ((r >> 1) & 3)) << 4));
+      const float4 ad = a[4 * hlf + k];
+      t.x += ad.x; t.y += ad.y; t.z += ad.z; t.w += ad.w;
+      const int m = m_warp + r;
+      if (m < p.M)
+        *reinterpret_cast<float4*>(static_cast<float*>(p.D) + static_cast<int64_t>(m) * p.ldd + nb + 16 * hlf + 4 * c) = t;
+    }
+  }
+}
+
 // Fetch the residual addend / ReLU-mask words of one chunk (issued before the TMEM wait).
 template <int CW>
 __device__ __forceinline__ void gemm_epilogue_prefetch(const GemmParams& p, float (&addv)[CW], uint32_t (&maskw)[CW / 2],

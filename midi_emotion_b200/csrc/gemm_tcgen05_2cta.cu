@@ -23,7 +23,9 @@ constexpr int G2_B_BYTES = 128 * G2_BK * 2;          // per CTA: its half of the
 constexpr int G2_STAGE_BYTES = G2_A_BYTES + G2_B_BYTES;
 constexpr int G2_EPI_THREADS = 256;
 constexpr int G2_THREADS = 64 + G2_EPI_THREADS;
-constexpr int G2_SMEM = G2_STAGES * G2_STAGE_BYTES + (2 * G2_STAGES + 5) * 8 + 16 + 2 * G2_BN * 4 + 1024;
+constexpr int G2_TRANSPOSE_BYTES = (G2_EPI_THREADS / 32) * 2048;  // per-warp scratch of the coalesced fp32 epilogue
+constexpr int G2_SMEM = G2_STAGES * G2_STAGE_BYTES + (2 * G2_STAGES + 5) * 8 + 16 + 2 * G2_BN * 4 + 16 +
+                        G2_TRANSPOSE_BYTES + 1024;
 constexpr uint32_t G2_PEER_MASK = 0xFEFFFFFFu;       // clears the CTA-rank bit of a shared::cluster address
 
 __device__ __forceinline__ uint32_t cluster_ctarank() {
@@ -80,6 +82,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   uint64_t* mask_bar = tempty_bar + 2;           // mask tile landed in the staging buffer (STAGED + mask)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(mask_bar + 1);
   float* bias_s = reinterpret_cast<float*>(tmem_slot + 4);  // [2][G2_BN]
+  uint8_t* transpose_s = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(bias_s + 2 * G2_BN) + 15) & ~uintptr_t(15));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t rank = cluster_ctarank();
@@ -264,6 +267,19 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             for (int e = 0; e < 4; ++e) h2[e] = __floats2bfloat162_rn(v[8 * j + 2 * e], v[8 * j + 2 * e + 1]);
             *reinterpret_cast<uint4*>(srow + (((q0 + j) ^ (row_in_tile & 7)) << 4)) = u;
           }
+        } else if (p.out_dtype == ME_F32 && p.splits == 1 && full && (p.ldd % 4 == 0)) {
+          // fp32 rows (residual-stream gradients, weight gradients without split-K): full-sector stores
+          float4 addc[8];
+          gemm_addend_coalesced(p, (p.flags & ME_EPI_ADD_F32) != 0, m0 + quarter * 32, nb, lane, addc);
+          gemm_epilogue_prefetch<CW>(p, addv, maskw, false, do_mask, m, nb, full);
+          tc_wait_ld();
+          float bsl[CW], v[CW];
+          if (use_bias) {
+#pragma unroll
+            for (int j = 0; j < CW; ++j) bsl[j] = bs[c0 + j];
+          }
+          gemm_epilogue_math<CW>(p, r, bsl, addv, maskw, use_bias, false, do_mask, v);
+          gemm_store_f32_coalesced(p, v, addc, m0 + quarter * 32, nb, transpose_s + (warp - 2) * 2048, lane);
         } else {
           gemm_epilogue_prefetch<CW>(p, addv, maskw, do_add, do_mask, m, nb, full);
           tc_wait_ld();
