@@ -126,6 +126,16 @@ int me_colsum(const void* X, int dtype, int M, int N, int ldx, float* out, void*
 int me_convert_2d(const void* src, int src_dtype, int ld_src, void* dst, int dst_dtype, int ld_dst, int rows,
                   int cols, void* stream);
 
+/* The same for a whole table of copies in ONE launch (the refresh of the compute-type weight copies at
+ * every forward pass: the reference re-casts its fp32 parameters under autocast on every call too,
+ * train.py:281).  `table_dev` is a DEVICE array of n entries, owned by the caller. */
+typedef struct me_convert_desc {
+  const void* src;
+  void* dst;
+  int32_t rows, cols, ld_src, ld_dst, src_dtype, dst_dtype;
+} me_convert_desc;
+int me_convert_batched(const me_convert_desc* table_dev, int n, void* stream);
+
 /* ---------------------------------------------------------------------------------------
  * Relative global attention (Music Transformer), causal + key-pad mask, fused:
  *   S[i,j] = (q_i.k_j + q_i.E[max_seq-1-(i-j)]) / sqrt(dh),  j <= i and !keypad[b,j]

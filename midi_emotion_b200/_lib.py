@@ -43,6 +43,11 @@ _LAYER_PTRS = ["x_f32", "x_T", "keypad", "Wqkv", "bqkv", "E", "Wo", "bo", "ln1_w
                "z2", "mean2", "rstd2", "out2_f32", "out2_T", "stream"]
 
 
+class ConvertDesc(C.Structure):
+    _fields_ = [("src", _vp), ("dst", _vp), ("rows", _i32), ("cols", _i32), ("ld_src", _i32), ("ld_dst", _i32),
+                ("src_dtype", _i32), ("dst_dtype", _i32)]
+
+
 class LayerArgs(C.Structure):
     _fields_ = [
         ("dtype", _i32), ("attn_impl", _i32), ("training", _i32), ("_pad0", _i32),
@@ -88,6 +93,7 @@ _PROTOS = {
     "me_add_layernorm_backward": (C.c_int, [_vp] * 6 + [C.c_int, C.c_int, _f32, _u64, C.c_int] + [_vp] * 5),
     "me_colsum": (C.c_int, [_vp, C.c_int, C.c_int, C.c_int, C.c_int, _vp, _vp]),
     "me_convert_2d": (C.c_int, [_vp, C.c_int, C.c_int, _vp, C.c_int, C.c_int, C.c_int, C.c_int, _vp]),
+    "me_convert_batched": (C.c_int, [_vp, C.c_int, _vp]),
     "me_attention_forward": (C.c_int, [C.POINTER(AttnArgs)]),
     "me_attention_backward": (C.c_int, [C.POINTER(AttnBwdArgs)]),
     "me_attention_backward_workspace_floats": (C.c_int64, [C.c_int] * 5),

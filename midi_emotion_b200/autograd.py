@@ -67,7 +67,7 @@ def run_forward(model, tokens: torch.Tensor, cond: Optional[torch.Tensor], need_
     if Ls > model.max_seq:
         raise RuntimeError(f"midi_emotion_b200: sequence length {Ls} exceeds max_seq {model.max_seq}")
     M = B * Ls
-    wc = model._weights(dtype)
+    wc = model._weights(dtype, refresh=True)
     stream = _stream()
     a = _Acts()
     a.dtype, a.B, a.L, a.Ls, a.M = dtype, B, L, Ls, M

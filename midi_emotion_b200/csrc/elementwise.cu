@@ -647,6 +647,52 @@ extern "C" int me_convert_2d(const void* src, int src_dtype, int ld_src, void* d
   return 0;
 }
 
+// One launch for a whole table of 2-D copies/casts (the per-step refresh of the compute-type weight copies).
+// blockIdx.y = table entry, blockIdx.x strides over its 4-element groups.
+template <typename TS, typename TD>
+__device__ __forceinline__ void convert_entry(const me_convert_desc& e) {
+  const TS* src = static_cast<const TS*>(e.src);
+  TD* dst = static_cast<TD*>(e.dst);
+  const bool vec = (e.cols % 4 == 0) && (e.ld_src % 4 == 0) && (e.ld_dst % 4 == 0) && e.cols == e.ld_dst &&
+                   ((reinterpret_cast<uintptr_t>(src) | reinterpret_cast<uintptr_t>(dst)) & 15) == 0;
+  if (vec) {
+    const int q = e.cols / 4;
+    const int64_t total = static_cast<int64_t>(e.rows) * q;
+    for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+         i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+      const int64_t r = i / q;
+      const int c = static_cast<int>(i - r * q) * 4;
+      float v[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) v[k] = to_f32<TS>(src[r * e.ld_src + c + k]);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) dst[r * e.ld_dst + c + k] = from_f32<TD>(v[k]);
+    }
+  } else {
+    const int64_t total = static_cast<int64_t>(e.rows) * e.ld_dst;
+    for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+         i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+      const int64_t r = i / e.ld_dst;
+      const int c = static_cast<int>(i - r * e.ld_dst);
+      dst[i] = from_f32<TD>(c < e.cols ? to_f32<TS>(src[r * e.ld_src + c]) : 0.f);
+    }
+  }
+}
+__global__ void convert_batched_kernel(const me_convert_desc* __restrict__ table) {
+  const me_convert_desc e = table[blockIdx.y];
+  if (e.src_dtype == ME_F32 && e.dst_dtype == ME_BF16) convert_entry<float, bf16>(e);
+  else if (e.src_dtype == ME_F32) convert_entry<float, float>(e);
+  else if (e.dst_dtype == ME_F32) convert_entry<bf16, float>(e);
+  else convert_entry<bf16, bf16>(e);
+}
+
+extern "C" int me_convert_batched(const me_convert_desc* table_dev, int n, void* stream) {
+  ME_CHECK(table_dev != nullptr && n > 0 && n <= 65535, "me_convert_batched: bad table (n = %d)", n);
+  convert_batched_kernel<<<dim3(sm_count() * 2, n), 256, 0, static_cast<cudaStream_t>(stream)>>>(table_dev);
+  ME_LAUNCH_CHECK();
+  return 0;
+}
+
 extern "C" int me_kv_cache_write(const void* qkv, int dtype, int B, int Ls, int H, int dh, void* k_cache,
                                  void* v_cache, int T_max, int pos0, void* stream) {
   ME_CHECK(pos0 >= 0 && pos0 + Ls <= T_max, "me_kv_cache_write: positions %d..%d exceed T_max %d", pos0,

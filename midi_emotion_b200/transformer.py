@@ -159,26 +159,26 @@ class MusicTransformer(nn.Module):
     def invalidate_weight_cache(self):
         self._wcache.clear()
 
-    def _weights(self, dtype: int) -> dict:
+    def _weights(self, dtype: int, refresh: bool = False) -> dict:
         """Packed device copies of the parameters in the compute type (QKV concatenated, bf16 casts).
-        Rebuilt whenever a parameter's version counter moved (optimiser step, load_state_dict)."""
+
+        `refresh=True` (every full forward pass) re-derives them from the fp32 parameters in one batched
+        launch -- the reference re-casts its parameters under autocast on every call as well, and parameter
+        version counters cannot be trusted to see an optimiser step (torch's fused Adam does not bump them).
+        Without `refresh` (backward of the same step, KV-cache decode steps) the copies are reused unless a
+        version counter or a storage pointer moved (load_state_dict, .to())."""
         params = self._param_list()
         versions = tuple(p._version for p in params) + tuple(p.data_ptr() for p in params)
         wc = self._wcache.get(dtype)
-        if wc is not None and wc["versions"] == versions:
+        if wc is not None and not refresh and wc["versions"] == versions:
             return wc
         dev = params[0].device
         tdt = torch.bfloat16 if dtype == ME_BF16 else torch.float32
         stream = torch.cuda.current_stream().cuda_stream
         d, di, V = self.embedding_dim, self.d_inner, self.vocab_size
-
-        def cast(dst, src):  # [rows, cols] fp32 parameter -> compute-type rows of dst
-            src = src.detach()
-            rows, cols = src.shape
-            _lib.call("me_convert_2d", ptr(src), ME_F32, cols, ptr(dst), dtype, dst.shape[1], rows, cols, stream)
-
-        if wc is None:
-            wc = {"layers": []}
+        ptrs = tuple(p.data_ptr() for p in params)
+        if wc is None or wc["ptrs"] != ptrs:
+            wc = {"layers": [], "ptrs": ptrs}
             for _ in range(self.num_layer):
                 wc["layers"].append({
                     "Wqkv": torch.empty(3 * d, d, device=dev, dtype=tdt),
@@ -189,17 +189,30 @@ class MusicTransformer(nn.Module):
                     "W2": torch.empty(d, di, device=dev, dtype=tdt),
                 })
             wc["Wfc"] = torch.empty(V, d, device=dev, dtype=tdt)
-        with torch.no_grad():
+            # table of (fp32 parameter -> compute-type copy) pairs for me_convert_batched
+            entries = []
+
+            def add(dst, src, dst_dtype):
+                src = src.detach()
+                rows, cols = (src.shape if src.dim() == 2 else (1, src.shape[0]))
+                ld_dst = dst.shape[1] if dst.dim() == 2 else cols
+                entries.append((src.data_ptr(), dst.data_ptr(), rows, cols, cols, ld_dst, ME_F32, dst_dtype))
+
             for l, lay in enumerate(self.enc_layers):
                 w = wc["layers"][l]
                 for i, lin in enumerate((lay.rga.Wq, lay.rga.Wk, lay.rga.Wv)):
-                    cast(w["Wqkv"][i * d:(i + 1) * d], lin.weight)
-                    w["bqkv"][i * d:(i + 1) * d].copy_(lin.bias)
-                cast(w["E"], lay.rga.E)
-                cast(w["Wo"], lay.rga.fc.weight)
-                cast(w["W1"], lay.FFN_pre.weight)
-                cast(w["W2"], lay.FFN_suf.weight)
-            cast(wc["Wfc"], self.fc.weight)
+                    add(w["Wqkv"][i * d:(i + 1) * d], lin.weight, dtype)
+                    add(w["bqkv"][i * d:(i + 1) * d], lin.bias, ME_F32)
+                add(w["E"], lay.rga.E, dtype)
+                add(w["Wo"], lay.rga.fc.weight, dtype)
+                add(w["W1"], lay.FFN_pre.weight, dtype)
+                add(w["W2"], lay.FFN_suf.weight, dtype)
+            add(wc["Wfc"], self.fc.weight, dtype)
+            table = (_lib.ConvertDesc * len(entries))(*[_lib.ConvertDesc(*e) for e in entries])
+            raw = torch.frombuffer(bytearray(bytes(table)), dtype=torch.uint8)
+            wc["table"] = raw.to(dev)
+            wc["n"] = len(entries)
+        _lib.call("me_convert_batched", ptr(wc["table"]), wc["n"], stream)
         wc["versions"] = versions
         self._wcache[dtype] = wc
         return wc

@@ -174,3 +174,22 @@ def test_dropout_training_runs_and_is_seed_dependent(golden):
         c = model(tokens, cond)
         d = model(tokens, cond)
     assert torch.equal(c, d)
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_fused_optimizer_step_reaches_the_next_forward(golden, precision):
+    """torch's fused Adam updates parameters without bumping their version counters: the compute-type weight
+    copies must be re-derived at every forward pass anyway (the reference re-casts under autocast per call)."""
+    g = golden
+    model = _model(g, precision).train()
+    tok, cond, tgt = g["tokens"].cuda(), g["cond"].cuda(), g["target"].cuda()
+    opt = torch.optim.Adam(model.parameters(), lr=1e-2, fused=True)
+    before = model(tok, cond).detach().float()
+    loss = torch.nn.functional.cross_entropy(model(tok, cond).float().reshape(-1, before.size(-1)), tgt.reshape(-1),
+                                             ignore_index=0)
+    loss.backward()
+    opt.step()
+    after = model(tok, cond).detach().float()
+    assert not torch.equal(before, after), "the optimiser step did not reach the kernels"
+    fresh = _model(dict(g, params=model.state_dict()), precision).train()
+    assert torch.equal(fresh(tok, cond).detach().float(), after)
