@@ -274,6 +274,36 @@ int me_embed_decode(const int64_t* tokens, const float* cond, const float* emb_w
                     int pad_token, const int32_t* t_dev, int dtype, float* x_f32, void* x_T, uint8_t* keypad,
                     int T_max, void* stream);
 
+/* ---------------------------------------------------------------------------------------
+ * Next-token sampling of the generation loop, generate.py:122-189, as one launch with no host round
+ * trips (the reference reads 2*B scalars back per generated token): NaN -> 0, special symbols -> -inf,
+ * log_softmax, temperature (temperatures[0] when the token just fed is a TIMESHIFT tuple, else
+ * temperatures[1]; plus the repeat penalty), top-k, top-p on the sorted cumulative softmax, softmax,
+ * draw, repeat-count update.  The draw is inverse-CDF over the descending-sorted kept set with one
+ * caller-supplied uniform in [0, 1) per sequence (torch.multinomial's generator stream is not
+ * reproducible outside PyTorch).  V <= 4096.
+ * ------------------------------------------------------------------------------------- */
+typedef struct me_sample_args {
+  int32_t B, V, ld_logits, logits_dtype; /* logits [B, ld_logits] T = ME_F32 | ME_BF16 (last position)     */
+  const void* logits;
+  const uint8_t* exclude;       /* [V] 1 = never sampled ("<...>" symbols, generate.py:57); may be NULL        */
+  const uint8_t* is_timeshift;  /* [V] 1 = tuple token whose event is a TIMESHIFT (generate.py:143-147); NULL ok */
+  const int64_t* prev_tokens;   /* [B] the token fed at this step (generate.py:140); NULL = rest temperature     */
+  float temp_note, temp_rest;   /* temperatures[0], temperatures[1]                                             */
+  float penalty_coeff;          /* generate.py:155-160; <= 0 disables                                           */
+  int32_t top_k;                /* <= 0 or > V: all                                                             */
+  float top_p;                  /* outside (0, 1): disabled                                                     */
+  int32_t _pad;
+  int32_t* repeat_counts;       /* [B] in/out (generate.py:185-189); may be NULL                                */
+  const float* uniforms;        /* [B] in [0, 1)                                                                */
+  int64_t* out_tokens;          /* [B]                                                                          */
+  int32_t* out_num_choices;     /* [B] entries with non-zero probability; may be NULL                           */
+  float* out_probs;             /* [B, V] final probabilities by token id; may be NULL (tests)                  */
+  void* stream;
+} me_sample_args;
+int me_sample_step(const me_sample_args* a);
+int me_sizeof_sample_args(void);
+
 #ifdef __cplusplus
 }
 #endif

@@ -8,5 +8,7 @@ Public surface (mirrors the reference's models package):
 from .build_model import build_model, CONDITIONINGS  # noqa: F401
 from .transformer import MusicTransformer, positional_table, set_dropout  # noqa: F401
 from .decode import KVCacheDecoder  # noqa: F401
+from .sampling import Sampler, generate  # noqa: F401
 
-__all__ = ["build_model", "MusicTransformer", "KVCacheDecoder", "set_dropout", "positional_table", "CONDITIONINGS"]
+__all__ = ["build_model", "MusicTransformer", "KVCacheDecoder", "Sampler", "generate", "set_dropout",
+           "positional_table", "CONDITIONINGS"]

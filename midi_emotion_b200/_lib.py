@@ -48,6 +48,14 @@ class ConvertDesc(C.Structure):
                 ("src_dtype", _i32), ("dst_dtype", _i32)]
 
 
+class SampleArgs(C.Structure):
+    _fields_ = [("B", _i32), ("V", _i32), ("ld_logits", _i32), ("logits_dtype", _i32), ("logits", _vp),
+                ("exclude", _vp), ("is_timeshift", _vp), ("prev_tokens", _vp), ("temp_note", _f32),
+                ("temp_rest", _f32), ("penalty_coeff", _f32), ("top_k", _i32), ("top_p", _f32), ("_pad", _i32),
+                ("repeat_counts", _vp), ("uniforms", _vp), ("out_tokens", _vp), ("out_num_choices", _vp),
+                ("out_probs", _vp), ("stream", _vp)]
+
+
 class LayerArgs(C.Structure):
     _fields_ = [
         ("dtype", _i32), ("attn_impl", _i32), ("training", _i32), ("_pad0", _i32),
@@ -77,6 +85,8 @@ _PROTOS = {
     "me_profile_enable": (C.c_int, [C.c_int]),
     "me_profile_collect": (C.c_int, [C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_int)]),
     "me_debug_trace_set": (C.c_int, [_vp]),
+    "me_sample_step": (C.c_int, [_vp]),
+    "me_sizeof_sample_args": (C.c_int, []),
     "me_sizeof_attn_args": (C.c_int, []),
     "me_sizeof_attn_bwd_args": (C.c_int, []),
     "me_sizeof_layer_args": (C.c_int, []),
@@ -145,7 +155,7 @@ def load(build_if_missing: bool = True):
                 fn.argtypes = args
         for cname, st in (("me_sizeof_attn_args", AttnArgs), ("me_sizeof_attn_bwd_args", AttnBwdArgs),
                           ("me_sizeof_layer_args", LayerArgs), ("me_sizeof_layer_bwd_args", LayerBwdArgs),
-                          ("me_sizeof_decode_layer_args", DecodeLayerArgs)):
+                          ("me_sizeof_decode_layer_args", DecodeLayerArgs), ("me_sizeof_sample_args", SampleArgs)):
             if getattr(lib, cname)() != C.sizeof(st):
                 raise RuntimeError(f"midi_emotion_b200: struct mirror {st.__name__} does not match the library")
         _lib = lib

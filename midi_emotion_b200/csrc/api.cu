@@ -140,6 +140,7 @@ extern "C" int me_sizeof_attn_bwd_args(void) { return static_cast<int>(sizeof(me
 extern "C" int me_sizeof_layer_args(void) { return static_cast<int>(sizeof(me_layer_args)); }
 extern "C" int me_sizeof_layer_bwd_args(void) { return static_cast<int>(sizeof(me_layer_bwd_args)); }
 extern "C" int me_sizeof_decode_layer_args(void) { return static_cast<int>(sizeof(me_decode_layer_args)); }
+extern "C" int me_sizeof_sample_args(void) { return static_cast<int>(sizeof(me_sample_args)); }
 
 // ---------------------------------------------------------------------------------------------
 // Live kernel timing for bench.py: while enabled, every tcgen05 GEMM launch is bracketed by CUDA

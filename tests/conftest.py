@@ -15,7 +15,22 @@ def pytest_configure(config):
 
 
 def golden_names():
-    return sorted(f[:-4] for f in os.listdir(GOLDEN_DIR) if f.endswith(".npz") and not f.startswith("pe_"))
+    return sorted(f[:-4] for f in os.listdir(GOLDEN_DIR)
+                  if f.endswith(".npz") and not f.startswith("pe_") and not f.startswith("sampling_"))
+
+
+def sampling_golden_names():
+    return sorted(f[:-4] for f in os.listdir(GOLDEN_DIR) if f.startswith("sampling_") and f.endswith(".npz"))
+
+
+def load_sampling_golden(name):
+    import numpy as np
+    import torch
+
+    z = np.load(os.path.join(GOLDEN_DIR, name + ".npz"))
+    g = {k: (torch.from_numpy(z[k]) if z[k].ndim else z[k].item()) for k in z.files}
+    g["temperatures"] = [float(x) for x in z["temperatures"]]
+    return g
 
 
 def load_golden(name):
@@ -47,3 +62,8 @@ def load_golden(name):
 @pytest.fixture(params=golden_names())
 def golden(request):
     return load_golden(request.param)
+
+
+@pytest.fixture(params=sampling_golden_names())
+def sampling_golden(request):
+    return load_sampling_golden(request.param)
