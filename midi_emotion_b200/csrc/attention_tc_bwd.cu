@@ -154,11 +154,12 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   uint64_t* q_free = bars + 7;    // dK accumulated, dE tile ready: Q is free
   uint64_t* e_free = bars + 8;    // the relative part of dQ is done: the band of E is free
   uint64_t* m2_done = bars + 9;   // dV accumulated, dQ tile ready: every MMA of the step has retired (dO, P free)
-  uint64_t* b_done = bars + 10;   // TMEM tiles of the step read out (256 arrivals)
+  uint64_t* b_done = bars + 10;   // dQ tile (and the dE rows in the dK columns) read out of TMEM (256 arrivals)
   uint64_t* stg_full = bars + 11; // dQ / dE tiles staged in shared memory (256 arrivals)
   uint64_t* stg_free = bars + 12; // the reduce-adds of the step have read the staging buffers
   uint64_t* p_free = bars + 13;   // ... the part of them that aliases P
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 14);
+  uint64_t* de_read = bars + 14;  // dE rows 0..127 (aliasing R) read out of TMEM (256 arrivals)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 15);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int kt = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
@@ -188,6 +189,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     mbar_init(e_free, 1);
     mbar_init(m2_done, 1);
     mbar_init(b_done, FB_COMPUTE_THREADS);
+    mbar_init(de_read, FB_COMPUTE_THREADS);
     mbar_init(stg_full, FB_COMPUTE_THREADS);
     mbar_init(stg_free, 1);
     mbar_init(p_free, 1);
@@ -230,16 +232,14 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         umma_bf16(tmem_base + FB_COL_DP, make_smem_desc_sw128(do_addr + k * 32, 16, 1024),
                   make_smem_desc_sw128(v_addr + k * 32, 16, 1024), idesc_s, k > 0);
     };
-    mbar_wait(kv_full, 0);
-    for (int st = 0; st < nsteps; ++st) {
-      const uint32_t ph = st & 1;
-      FB_TRACE(2, st, 0);
-      mbar_wait(q_full, ph);
-      mbar_wait(e_full, ph);
-      FB_TRACE(2, st, 1);
-      if (st > 0) mbar_wait(b_done, (st - 1) & 1);  // S / R (and the dE alias) may be overwritten
+    // [S | R] of step st only overwrites TMEM that the threads release early (S, R in phase A; the dE rows
+    // aliasing R at q_free time), so it is queued directly behind the MMAs of step st-1: the tensor pipe
+    // never waits for the threads to drain the dQ tile.
+    auto issue_sr = [&](int st) {
+      mbar_wait(q_full, st & 1);
+      mbar_wait(e_full, st & 1);
+      if (st > 0) mbar_wait(de_read, (st - 1) & 1);
       tc_fence_after();
-      FB_TRACE(2, st, 2);
       if (elect_one()) {
 #pragma unroll
         for (int k = 0; k < DH / 16; ++k)  // [S | R] = Q [K ; Eband]^T
@@ -248,15 +248,21 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         umma_commit(m1_done);
       }
       __syncwarp();
-      mbar_wait(do_full, ph);
+      mbar_wait(do_full, st & 1);
       tc_fence_after();
       if (elect_one()) {
         issue_dp();  // (its TMEM columns were consumed before a_done of the previous step)
         umma_commit(dp_done);
       }
       __syncwarp();
+    };
+    mbar_wait(kv_full, 0);
+    issue_sr(0);
+    for (int st = 0; st < nsteps; ++st) {
+      const uint32_t ph = st & 1;
       FB_TRACE(2, st, 3);
       mbar_wait(a_done, ph);
+      if (st > 0) mbar_wait(b_done, (st - 1) & 1);  // the dQ tile and the dE rows in the dK columns were read out
       tc_fence_after();
       FB_TRACE(2, st, 4);
       const uint32_t acc0 = st > 0 ? 1u : 0u;
@@ -288,6 +294,8 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       }
       __syncwarp();
       FB_TRACE(2, st, 5);
+      if (st + 1 < nsteps) issue_sr(st + 1);
+      FB_TRACE(2, st, 6);
     }
   } else if (warp == FB_LOAD_WARP) {
     // ======================= TMA loads =======================
@@ -504,6 +512,8 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         tmem_ld_cols<HC>(t_lane + FB_COL_DE_LO + half * HC, lo);
         if (quarter >= 2) tmem_ld_cols<HC>(t_lane + FB_COL_DK + half * HC, hi);
         tc_wait_ld();
+        tc_fence_before();
+        mbar_arrive(de_read);   // the next [S | R] may overwrite the R columns
         if (quarter >= 2) tmem_zero_cols<HC>(t_lane + FB_COL_DK + half * HC);  // next step accumulates onto zeros
         sts_row_swz<HC, SWZ>(stg1 + a * STG, a, half * (HC / 4), lo);
       }
@@ -512,7 +522,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       tc_fence_after();
       FB_TRACE(trole, st, 8);
       {
-        // release the TMEM tiles before the (slower) staging stores: the next [S | R] MMAs wait for that
+        // release the dQ columns before the (slower) staging stores
         uint32_t dq[HC];
         tmem_ld_cols<HC>(t_lane + FB_COL_DQ + half * HC, dq);
         tc_wait_ld();
