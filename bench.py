@@ -216,6 +216,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--attn", default="auto", choices=["auto", "simt", "tensor"])
     ap.add_argument("--no-decode", action="store_true", help="skip the KV-cache decode measurement (configs[3])")
+    ap.add_argument("--torch-loss", action="store_true", help="PyTorch cross-entropy instead of the fused kernel")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -227,7 +228,7 @@ def main():
         raise SystemExit("bench.py: no CUDA device (the B200 path has no CPU fallback)")
 
     import torch.distributed as dist
-    from midi_emotion_b200 import _lib, build_model
+    from midi_emotion_b200 import _lib, build_model, cross_entropy
     from midi_emotion_b200.ddp import DataParallel
 
     torch.cuda.set_device(local_rank)
@@ -256,8 +257,11 @@ def main():
     def train_step(tokens, cond, target):
         with torch.autocast("cuda", dtype=torch.bfloat16):
             logits = model(tokens, cond)
-        loss = torch.nn.functional.cross_entropy(logits.reshape(-1, logits.size(-1)).float(), target.reshape(-1),
-                                                 ignore_index=0)
+        if args.torch_loss:   # the reference's nn.CrossEntropyLoss (train.py:124,288-290) on the logits
+            loss = torch.nn.functional.cross_entropy(logits.reshape(-1, logits.size(-1)).float(), target.reshape(-1),
+                                                     ignore_index=0)
+        else:                 # the same loss, fused with its gradient and the top-k counts (me_cross_entropy)
+            loss = cross_entropy(logits, target, ignore_index=0)
         loss.backward()
         ddp.sync_gradients()
         torch.nn.utils.clip_grad_norm_(model.parameters(), 1.0)
@@ -330,7 +334,7 @@ def main():
                                    "seq1024 batch32/GPU bf16 (BASELINE configs[1])",
                        "global_batch": world * B, "seq_len": L, "parallelism": f"dp{world}",
                        "l2": "per-step working set (activations > 10 GB) far exceeds the 126 MB L2; no flush needed",
-                       "attention": args.attn, "final_loss": final_loss},
+                       "attention": args.attn, "loss": "torch" if args.torch_loss else "fused", "final_loss": final_loss},
             "e2e": {"value": e2e, "unit": "tokens/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
                     "ms_per_step": ms_e2e / K},
             "gpu_launches": int(launches),

@@ -304,6 +304,18 @@ typedef struct me_sample_args {
 int me_sample_step(const me_sample_args* a);
 int me_sizeof_sample_args(void);
 
+/* ---------------------------------------------------------------------------------------
+ * Fused cross-entropy over the output head's logits: train.py:124,288-290 (CrossEntropyLoss with
+ * ignore_index = pad, mean over the non-pad targets), its gradient, and the top-1 / top-5 hit counts of
+ * utils.accuracy (utils.py:15-80, used at train.py:256), in one pass.
+ *   logits T [M, ld] (V valid columns), targets int64 [M]
+ *   grad_logits T [M, ld_grad] or NULL: d(mean loss)/d(logits); columns >= V are zeroed; may alias logits
+ *   stats f32 [4] out: { sum of per-row losses, number of non-ignored rows, top-1 hits, top-5 hits }
+ *   (mean loss = stats[0] / stats[1]; a target counts as a top-k hit when fewer than k logits are larger)
+ * ------------------------------------------------------------------------------------- */
+int me_cross_entropy(const void* logits, int dtype, int M, int V, int ld, const int64_t* targets,
+                     int64_t ignore_index, void* grad_logits, int ld_grad, float* stats, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

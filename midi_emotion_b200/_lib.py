@@ -86,6 +86,7 @@ _PROTOS = {
     "me_profile_collect": (C.c_int, [C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_int)]),
     "me_debug_trace_set": (C.c_int, [_vp]),
     "me_sample_step": (C.c_int, [_vp]),
+    "me_cross_entropy": (C.c_int, [_vp, C.c_int, C.c_int, C.c_int, C.c_int, _vp, C.c_int64, _vp, C.c_int, _vp, _vp]),
     "me_sizeof_sample_args": (C.c_int, []),
     "me_sizeof_attn_args": (C.c_int, []),
     "me_sizeof_attn_bwd_args": (C.c_int, []),

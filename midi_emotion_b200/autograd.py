@@ -140,14 +140,28 @@ def run_forward(model, tokens: torch.Tensor, cond: Optional[torch.Tensor], need_
     return logits, a
 
 
-def run_backward(model, tokens, cond, a: _Acts, g_logits: torch.Tensor) -> List[Optional[torch.Tensor]]:
-    """g_logits: [M, Vp] in the compute type (pad columns zero).  Returns gradients in
-    named_parameters() order."""
+def _uniform_row_pitch(t: torch.Tensor):
+    """Row pitch (elements) when t[..., V] is M rows of V contiguous elements at one pitch, else None."""
+    if t.dim() < 2 or t.stride(-1) != 1:
+        return None
+    ld = t.stride(-2)
+    expect = ld
+    for size, stride in zip(reversed(t.shape[:-1]), reversed(t.stride()[:-1])):
+        if size != 1 and stride != expect:
+            return None
+        expect *= size
+    return ld if ld >= t.shape[-1] else None
+
+
+def run_backward(model, tokens, cond, a: _Acts, g_logits: torch.Tensor, ld_g: Optional[int] = None) -> List[Optional[torch.Tensor]]:
+    """g_logits: M rows of V gradient values in the compute type at row pitch ld_g (default Vp; columns >= V are
+    never read).  Returns gradients in named_parameters() order."""
     dtype = a.dtype
     tdt = _tdtype(dtype)
     dev = tokens.device
     B, L, Ls, M = a.B, a.L, a.Ls, a.M
     d, di, H, V, Vp = model.embedding_dim, model.d_inner, model.num_head, model.vocab_size, a.Vp
+    ld_g = ld_g or Vp
     dh = d // H
     wc = model._weights(dtype)
     stream = _stream()
@@ -174,16 +188,16 @@ def run_backward(model, tokens, cond, a: _Acts, g_logits: torch.Tensor) -> List[
     gh["fc.bias"].zero_()
     grads.update(gh)
     d_x = torch.empty(M, d, **f32)
-    _lib.call("me_colsum", ptr(g_logits), dtype, M, V, Vp, ptr(grads["fc.bias"]), stream)
+    _lib.call("me_colsum", ptr(g_logits), dtype, M, V, ld_g, ptr(grads["fc.bias"]), stream)
     if dtype == ME_BF16:
-        _lib.call("me_gemm_bf16", ptr(g_logits), ptr(last["out2_T"]), ptr(grads["fc.weight"]), V, d, M, Vp, d, d, 1, 1,
+        _lib.call("me_gemm_bf16", ptr(g_logits), ptr(last["out2_T"]), ptr(grads["fc.weight"]), V, d, M, ld_g, d, d, 1, 1,
                   ME_F32, 0, None, None, None, 0, stream)
-        _lib.call("me_gemm_bf16", ptr(g_logits), ptr(wc["Wfc"]), ptr(d_x), M, d, V, Vp, d, d, 0, 1, ME_F32, 0, None,
+        _lib.call("me_gemm_bf16", ptr(g_logits), ptr(wc["Wfc"]), ptr(d_x), M, d, V, ld_g, d, d, 0, 1, ME_F32, 0, None,
                   None, None, 0, stream)
     else:
-        _lib.call("me_gemm_f32", ptr(g_logits), ptr(last["out2_T"]), ptr(grads["fc.weight"]), V, d, M, Vp, d, d, 1, 1,
+        _lib.call("me_gemm_f32", ptr(g_logits), ptr(last["out2_T"]), ptr(grads["fc.weight"]), V, d, M, ld_g, d, d, 1, 1,
                   0, None, None, None, 0, stream)
-        _lib.call("me_gemm_f32", ptr(g_logits), ptr(wc["Wfc"]), ptr(d_x), M, d, V, Vp, d, d, 0, 1, 0, None, None,
+        _lib.call("me_gemm_f32", ptr(g_logits), ptr(wc["Wfc"]), ptr(d_x), M, d, V, ld_g, d, d, 0, 1, 0, None, None,
                   None, 0, stream)
     if hook is not None:
         hook(flat_head)
@@ -271,14 +285,23 @@ class _ModelFn(torch.autograd.Function):
             raise RuntimeError("midi_emotion_b200: backward called twice or forward ran without grad")
         V, Vp, M = model.vocab_size, a.Vp, a.M
         tdt = _tdtype(a.dtype)
-        src_dt = {torch.float32: ME_F32, torch.bfloat16: ME_BF16}.get(g_out.dtype)
-        if src_dt is None:
-            g_out = g_out.float()
-            src_dt = ME_F32
-        g_out = g_out.contiguous()
-        g_logits = torch.empty(M, Vp, device=g_out.device, dtype=tdt)
-        _lib.call("me_convert_2d", ptr(g_out), src_dt, V, ptr(g_logits), a.dtype, Vp, M, V, _stream())
-        grads = run_backward(model, ctx.tokens, ctx.cond, a, g_logits)
+        ld = _uniform_row_pitch(g_out)
+        align = 8 if tdt == torch.bfloat16 else 4
+        if g_out.dtype == tdt and ld is not None and ld % align == 0 and g_out.data_ptr() % 16 == 0:
+            # already in the compute type with one 16-byte aligned row pitch (e.g. the fused cross-entropy's
+            # gradient, which keeps the logits' padded pitch): the GEMMs read it in place -- columns >= V are
+            # never touched (TMA bounds), so they need not be zero
+            g_logits, ld_g = g_out, ld
+        else:
+            src_dt = {torch.float32: ME_F32, torch.bfloat16: ME_BF16}.get(g_out.dtype)
+            if src_dt is None:
+                g_out = g_out.float()
+                src_dt = ME_F32
+            g_out = g_out.contiguous()
+            g_logits = torch.empty(M, Vp, device=g_out.device, dtype=tdt)
+            _lib.call("me_convert_2d", ptr(g_out), src_dt, V, ptr(g_logits), a.dtype, Vp, M, V, _stream())
+            ld_g = Vp
+        grads = run_backward(model, ctx.tokens, ctx.cond, a, g_logits, ld_g)
         ctx.acts = None
         return (None, None, None, None, *grads)
 

@@ -1,0 +1,82 @@
+"""Fused cross-entropy for the training step (replaces `self.ce_loss(output_flat, target)` at train.py:288-290 and
+the top-k accuracy of utils.accuracy at train.py:256): loss, gradient w.r.t. the logits and the top-1 / top-5 hit
+counts in one pass over the logits (`me_cross_entropy`).  Drop-in:
+
+    loss = cross_entropy(output, target, ignore_index=pad_idx)           # output: [B, L, V] model logits
+    loss, stats = cross_entropy(output, target, ignore_index=pad_idx, return_stats=True)
+    # stats: {"count", "top1", "top5"} as 0-d device tensors (accuracies = top_k / count, no host sync here)
+"""
+from __future__ import annotations
+
+import torch
+
+from . import _lib
+from ._lib import ME_BF16, ME_F32, ptr
+
+
+def _rows(logits: torch.Tensor):
+    """View logits [..., V] as M rows with one pitch, without copying when it is a column slice of a padded
+    [M, Vp] buffer (what the model returns for V = 1007)."""
+    V = logits.shape[-1]
+    if logits.stride(-1) != 1:
+        logits = logits.contiguous()
+    if logits.dim() == 2:
+        return logits, logits.shape[0], V, logits.stride(0)
+    ld = logits.stride(-2)
+    ok = True
+    expect = ld
+    for size, stride in zip(reversed(logits.shape[:-1]), reversed(logits.stride()[:-1])):
+        if size != 1 and stride != expect:
+            ok = False
+            break
+        expect *= size
+    if not ok:
+        logits = logits.contiguous()
+        ld = V
+    return logits, logits.numel() // V, V, ld
+
+
+class _FusedCrossEntropy(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, logits, target, ignore_index):
+        if not logits.is_cuda:
+            raise RuntimeError("midi_emotion_b200: CUDA tensors required (there is no CPU fallback)")
+        dt = {torch.float32: ME_F32, torch.bfloat16: ME_BF16}.get(logits.dtype)
+        if dt is None:
+            raise RuntimeError("midi_emotion_b200: logits must be float32 or bfloat16")
+        x, M, V, ld = _rows(logits)
+        tgt = target.reshape(-1).contiguous()
+        if tgt.numel() != M or tgt.dtype != torch.int64:
+            raise RuntimeError("midi_emotion_b200: target must be int64 with one entry per logits row")
+        stats = torch.empty(4, device=x.device, dtype=torch.float32)
+        need_grad = logits.requires_grad
+        # the gradient keeps the logits' row pitch (padding columns zeroed), so that a padded-pitch consumer
+        # (the model's backward) can take it without a copy
+        grad = None
+        if need_grad:
+            base = torch.empty(M * ld, device=x.device, dtype=x.dtype)
+            grad = base.as_strided(x.shape, x.stride())
+        _lib.call("me_cross_entropy", ptr(x), dt, M, V, ld, ptr(tgt), int(ignore_index), ptr(grad), ld if need_grad else 0,
+                  ptr(stats), torch.cuda.current_stream().cuda_stream)
+        ctx.grad, ctx.shape = grad, logits.shape
+        ctx.mark_non_differentiable(stats)
+        loss = stats[0] / stats[1]
+        return loss, stats
+
+    @staticmethod
+    def backward(ctx, g_loss, _g_stats):
+        g = ctx.grad
+        ctx.grad = None
+        if g is None:
+            return None, None, None
+        # d(mean loss)/d(logits) was written by the forward kernel (row pitch of the logits kept, so the model's
+        # backward takes it without a copy); scale by the upstream gradient in place
+        g.mul_(g_loss)
+        return g.view(ctx.shape) if g.shape != ctx.shape else g, None, None
+
+
+def cross_entropy(logits: torch.Tensor, target: torch.Tensor, ignore_index: int = 0, return_stats: bool = False):
+    loss, stats = _FusedCrossEntropy.apply(logits, target, ignore_index)
+    if return_stats:
+        return loss, {"count": stats[1], "top1": stats[2], "top5": stats[3]}
+    return loss

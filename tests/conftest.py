@@ -16,7 +16,7 @@ def pytest_configure(config):
 
 def golden_names():
     return sorted(f[:-4] for f in os.listdir(GOLDEN_DIR)
-                  if f.endswith(".npz") and not f.startswith("pe_") and not f.startswith("sampling_"))
+                  if f.endswith(".npz") and not f.startswith(("pe_", "sampling_", "ce_")))
 
 
 def sampling_golden_names():
@@ -62,6 +62,19 @@ def load_golden(name):
 @pytest.fixture(params=golden_names())
 def golden(request):
     return load_golden(request.param)
+
+
+def ce_golden_names():
+    return sorted(f[:-4] for f in os.listdir(GOLDEN_DIR) if f.startswith("ce_") and f.endswith(".npz"))
+
+
+@pytest.fixture(params=ce_golden_names())
+def ce_golden(request):
+    import numpy as np
+    import torch
+
+    z = np.load(os.path.join(GOLDEN_DIR, request.param + ".npz"))
+    return {k: (torch.from_numpy(z[k]) if z[k].ndim else z[k].item()) for k in z.files}
 
 
 @pytest.fixture(params=sampling_golden_names())

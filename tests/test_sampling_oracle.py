@@ -36,3 +36,13 @@ def test_oracle_sampling_never_picks_excluded_and_keeps_the_top_entry():
     best = logits.clone()
     best[:, :5] = -float("inf")
     assert torch.equal(tokens, best.argmax(-1))
+
+
+def test_oracle_cross_entropy_and_accuracy_match_the_reference(ce_golden):
+    """oracle.ce_and_accuracy against nn.CrossEntropyLoss(ignore_index=0) (train.py:124) and the reference's own
+    utils.accuracy (scripts/make_golden_ce.py)."""
+    g = ce_golden
+    loss, grad, hits, count = O.ce_and_accuracy(g["logits"], g["target"], ignore_index=0)
+    assert abs(float(loss) - g["loss"]) < 1e-6 and count == g["count"]
+    assert torch.allclose(grad, g["grad"], rtol=1e-6, atol=1e-9)
+    assert hits[1] == g["top1"] and hits[5] == g["top5"]
