@@ -200,22 +200,28 @@ add_ln_fwd_kernel(const float* __restrict__ x_res, const T* __restrict__ y, cons
   }
   __syncthreads();
   for (int64_t row = warp0; row < M; row += nwarps) {
-    float z[NCH][4];
+    // All loads of the row are issued before the first use (no branches in between: the column guard is
+    // applied by clamping the address, a branch per chunk made the compiler serialise load -> use per chunk,
+    // i.e. one memory latency per chunk instead of one per row).
+    float z[NCH][4], yv[NCH][4];
     float sum = 0.f;
 #pragma unroll
     for (int k = 0; k < NCH; ++k) {
       const int c = 4 * (lane + 32 * k);
-      if (c < d) {
-        const int64_t idx = row * d + c;
-        float yv[4], xv[4], dm[4];
-        Vec4<T>::load(y + idx, yv);
-        Vec4<float>::load(x_res + idx, xv);
-        dropout_scale4(p, inv_keep, seed32, static_cast<uint64_t>(idx), dm);
+      const int64_t idx = row * d + (c < d ? c : 0);
+      Vec4<T>::load(y + idx, yv[k]);
+      Vec4<float>::load(x_res + idx, z[k]);
+    }
 #pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          z[k][e] = yv[e] * dm[e] + xv[e];
-          sum += z[k][e];
-        }
+    for (int k = 0; k < NCH; ++k) {
+      const int c = 4 * (lane + 32 * k);
+      const bool ok = c < d;
+      float dm[4];
+      dropout_scale4(p, inv_keep, seed32, static_cast<uint64_t>(row * d + c), dm);
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        z[k][e] = ok ? yv[k][e] * dm[e] + z[k][e] : 0.f;
+        sum += z[k][e];
       }
     }
     const float mean = warp_sum(sum) * inv_d;
@@ -279,25 +285,34 @@ add_ln_bwd_kernel(const float* __restrict__ dout, const float* __restrict__ dout
   const float inv_d = 1.f / static_cast<float>(d);
   const bool alias = static_cast<const void*>(dy_T) == static_cast<const void*>(dz_f32);
   for (int64_t row = warp0; row < M; row += nwarps) {
-    const float mu = mean[row], rs = rstd[row];
+    // all loads of the row first, branch-free (see the forward kernel)
     float dy[NCH][4], xh[NCH][4];
     float s1 = 0.f, s2 = 0.f;
 #pragma unroll
     for (int k = 0; k < NCH; ++k) {
       const int c = 4 * (lane + 32 * k);
-      if (c < d) {
-        const int64_t idx = row * d + c;
-        float zv[4];
-        Vec4<float>::load(dout + idx, dy[k]);
-        Vec4<float>::load(z + idx, zv);
-        if (dout_add) {
-          float t[4];
-          Vec4<float>::load(dout_add + idx, t);
+      const int64_t idx = row * d + (c < d ? c : 0);
+      Vec4<float>::load(dout + idx, dy[k]);
+      Vec4<float>::load(z + idx, xh[k]);
+    }
+    if (dout_add) {
 #pragma unroll
-          for (int e = 0; e < 4; ++e) dy[k][e] += t[e];
-        }
+      for (int k = 0; k < NCH; ++k) {
+        const int c = 4 * (lane + 32 * k);
+        float t[4];
+        Vec4<float>::load(dout_add + row * d + (c < d ? c : 0), t);
 #pragma unroll
-        for (int e = 0; e < 4; ++e) xh[k][e] = (zv[e] - mu) * rs;
+        for (int e = 0; e < 4; ++e) dy[k][e] += t[e];
+      }
+    }
+    const float mu = mean[row], rs = rstd[row];
+#pragma unroll
+    for (int k = 0; k < NCH; ++k) {
+      const bool ok = 4 * (lane + 32 * k) < d;
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        xh[k][e] = ok ? (xh[k][e] - mu) * rs : 0.f;
+        dy[k][e] = ok ? dy[k][e] : 0.f;
       }
     }
 #pragma unroll
