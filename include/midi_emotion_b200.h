@@ -122,6 +122,10 @@ int me_add_layernorm_backward(const float* dout, const float* dout_add, const fl
 
 /* column sums (bias gradients): out[n] += sum_m X[m, n]; X is T with row pitch ldx. */
 int me_colsum(const void* X, int dtype, int M, int N, int ldx, float* out, void* stream);
+/* the same with caller scratch (>= 148 * N floats, 16-byte aligned): partial rows + a finish pass instead of
+ * same-address atomics, which serialise in the L2; falls back to me_colsum when the shape does not fit. */
+int me_colsum_ws(const void* X, int dtype, int M, int N, int ldx, float* out, float* ws, int64_t ws_floats,
+                 void* stream);
 /* dst (T_dst, pitch ld_dst) = src (T_src, pitch ld_src), [rows, cols]; pad columns are zeroed. */
 int me_convert_2d(const void* src, int src_dtype, int ld_src, void* dst, int dst_dtype, int ld_dst, int rows,
                   int cols, void* stream);

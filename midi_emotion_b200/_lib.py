@@ -103,6 +103,7 @@ _PROTOS = {
     "me_add_layernorm_forward": (C.c_int, [_vp, _vp, C.c_int, _vp, _vp, _f32, C.c_int, C.c_int, _f32, _u64] + [_vp] * 6),
     "me_add_layernorm_backward": (C.c_int, [_vp] * 6 + [C.c_int, C.c_int, _f32, _u64, C.c_int] + [_vp] * 5),
     "me_colsum": (C.c_int, [_vp, C.c_int, C.c_int, C.c_int, C.c_int, _vp, _vp]),
+    "me_colsum_ws": (C.c_int, [_vp, C.c_int, C.c_int, C.c_int, C.c_int, _vp, _vp, C.c_int64, _vp]),
     "me_convert_2d": (C.c_int, [_vp, C.c_int, C.c_int, _vp, C.c_int, C.c_int, C.c_int, C.c_int, _vp]),
     "me_convert_batched": (C.c_int, [_vp, C.c_int, _vp]),
     "me_attention_forward": (C.c_int, [C.POINTER(AttnArgs)]),

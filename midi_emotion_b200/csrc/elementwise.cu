@@ -563,6 +563,70 @@ int launch_add_ln_bwd(const float* dout, const float* dout_add, const float* z, 
   return 0;
 }
 
+// Row-streaming variant for bf16 matrices whose width is a multiple of 256 (the bias-gradient sums of the
+// layer: [M, d_inner], [M, 3d]): like the LayerNorm kernels a warp reads whole rows -- NCH 16-byte loads per
+// lane, issued together, two rows in flight -- and keeps its 8*NCH column sums in registers.  Same-address
+// atomics from different SMs serialise at ~0.1 us each (measured: kernel time grew linearly with the number
+// of adds per column), so the block folds its warps in shared memory and writes ONE partial row to a
+// workspace; a second tiny kernel adds the partial rows into `out`.
+template <int NCH>
+__global__ void __launch_bounds__(256, 1)
+colsum_rows_kernel(const bf16* __restrict__ X, int M, int ldx, float* __restrict__ partial) {
+  __shared__ float fold[NCH * 256];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int64_t warp0 = static_cast<int64_t>(blockIdx.x) * 8 + warp;
+  const int64_t nwarps = static_cast<int64_t>(gridDim.x) * 8;
+  float acc[NCH][8];
+#pragma unroll
+  for (int k = 0; k < NCH; ++k)
+#pragma unroll
+    for (int e = 0; e < 8; ++e) acc[k][e] = 0.f;
+  for (int64_t row = warp0; row < M; row += 2 * nwarps) {
+    const bool two = row + nwarps < M;
+    const bf16* p0 = X + row * ldx + lane * 8;
+    const bf16* p1 = X + (two ? row + nwarps : row) * ldx + lane * 8;
+    uint4 u0[NCH], u1[NCH];
+#pragma unroll
+    for (int k = 0; k < NCH; ++k) {
+      u0[k] = *reinterpret_cast<const uint4*>(p0 + 256 * k);
+      u1[k] = *reinterpret_cast<const uint4*>(p1 + 256 * k);
+    }
+    const float w1 = two ? 1.f : 0.f;
+#pragma unroll
+    for (int k = 0; k < NCH; ++k) {
+      const uint32_t a[4] = {u0[k].x, u0[k].y, u0[k].z, u0[k].w};
+      const uint32_t b[4] = {u1[k].x, u1[k].y, u1[k].z, u1[k].w};
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        acc[k][2 * e] += __uint_as_float(a[e] << 16) + w1 * __uint_as_float(b[e] << 16);
+        acc[k][2 * e + 1] += __uint_as_float(a[e] & 0xFFFF0000u) + w1 * __uint_as_float(b[e] & 0xFFFF0000u);
+      }
+    }
+  }
+  for (int w = 0; w < 8; ++w) {   // fold the eight warps, one after the other
+    if (warp == w) {
+#pragma unroll
+      for (int k = 0; k < NCH; ++k) {
+        float4* f = reinterpret_cast<float4*>(fold + 256 * k + lane * 8);
+        float4 lo = w ? f[0] : make_float4(0.f, 0.f, 0.f, 0.f), hi = w ? f[1] : make_float4(0.f, 0.f, 0.f, 0.f);
+        lo.x += acc[k][0]; lo.y += acc[k][1]; lo.z += acc[k][2]; lo.w += acc[k][3];
+        hi.x += acc[k][4]; hi.y += acc[k][5]; hi.z += acc[k][6]; hi.w += acc[k][7];
+        f[0] = lo; f[1] = hi;
+      }
+    }
+    __syncthreads();
+  }
+  float* prow = partial + static_cast<int64_t>(blockIdx.x) * (NCH * 256);
+  for (int c = threadIdx.x; c < NCH * 256; c += 256) prow[c] = fold[c];
+}
+__global__ void colsum_finish_kernel(const float* __restrict__ partial, int rows, int N, float* __restrict__ out) {
+  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= N) return;
+  float s = 0.f;
+  for (int r = 0; r < rows; ++r) s += partial[static_cast<int64_t>(r) * N + n];
+  out[n] += s;
+}
+
 int launch_colsum(const void* X, int dtype, int M, int N, int ldx, float* out, cudaStream_t st) {
   const int threads = 64;
   const int vec = dtype == ME_BF16 ? 8 : 4;
@@ -579,6 +643,27 @@ int launch_colsum(const void* X, int dtype, int M, int N, int ldx, float* out, c
   ME_LAUNCH_CHECK();
   return 0;
 }
+
+// out[n] += column sums; `ws` (>= sm_count * N floats, 16-byte aligned) is optional scratch for the partial rows.
+int launch_colsum_ws(const void* X, int dtype, int M, int N, int ldx, float* out, float* ws, int64_t ws_floats,
+                     cudaStream_t st) {
+  const int blocks = sm_count();
+  if (ws && ws_floats >= static_cast<int64_t>(blocks) * N && dtype == ME_BF16 && N % 256 == 0 && N <= 3072 &&
+      ldx % 8 == 0 && (reinterpret_cast<uintptr_t>(X) & 15) == 0 && M >= 2048) {
+    const bf16* x = static_cast<const bf16*>(X);
+    switch (N / 256) {
+#define ME_CS(NC) case NC: colsum_rows_kernel<NC><<<blocks, 256, 0, st>>>(x, M, ldx, ws); break;
+      ME_CS(1) ME_CS(2) ME_CS(3) ME_CS(4) ME_CS(5) ME_CS(6) ME_CS(7) ME_CS(8) ME_CS(9) ME_CS(10) ME_CS(11) ME_CS(12)
+#undef ME_CS
+    }
+    ME_LAUNCH_CHECK();
+    colsum_finish_kernel<<<(N + 255) / 256, 256, 0, st>>>(ws, blocks, N, out);
+    ME_LAUNCH_CHECK();
+    return 0;
+  }
+  return launch_colsum(X, dtype, M, N, ldx, out, st);
+}
+
 
 }  // namespace me
 
@@ -634,6 +719,11 @@ extern "C" int me_add_layernorm_backward(const float* dout, const float* dout_ad
   ME_CHECK(M > 0 && d > 0 && d <= 1024, "me_add_layernorm_backward: bad dims");
   return launch_add_ln_bwd(dout, dout_add, z, mean, rstd, gamma, M, d, dropout_p, seed, dtype, dz_f32, dy_T,
                            d_gamma, d_beta, nullptr, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int me_colsum_ws(const void* X, int dtype, int M, int N, int ldx, float* out, float* ws, int64_t ws_floats,
+                            void* stream) {
+  return launch_colsum_ws(X, dtype, M, N, ldx, out, ws, ws_floats, static_cast<cudaStream_t>(stream));
 }
 
 extern "C" int me_colsum(const void* X, int dtype, int M, int N, int ldx, float* out, void* stream) {

@@ -17,7 +17,8 @@ int launch_add_ln_fwd(const float* x_res, const void* y, int dtype, const float*
 int launch_add_ln_bwd(const float* dout, const float* dout_add, const float* z, const float* mean,
                       const float* rstd, const float* gamma, int M, int d, float p, uint64_t seed, int dtype,
                       float* dz_f32, void* dy_T, float* d_gamma, float* d_beta, float* d_ybias, cudaStream_t st);
-int launch_colsum(const void* X, int dtype, int M, int N, int ldx, float* out, cudaStream_t st);
+int launch_colsum_ws(const void* X, int dtype, int M, int N, int ldx, float* out, float* ws, int64_t ws_floats,
+                     cudaStream_t st);
 int launch_kv_write(const void* qkv, int dtype, int B, int Ls, int H, int dh, void* kc, void* vc, int T_max,
                     int pos0, const int32_t* t_dev, cudaStream_t st);
 
@@ -153,7 +154,9 @@ extern "C" int me_layer_backward(const me_layer_bwd_args* b) {
   if (linear(dt, b->g_T, a->W2, b->g_h, M, di, d, d, di, di, 0, 1, false, ME_EPI_RELU_MASK, nullptr, nullptr, a->h,
              di, st))
     return 1;
-  if (launch_colsum(b->g_h, dt, M, di, di, b->db1, st)) return 1;
+  // (the attention workspace is idle outside me_attention_backward: scratch for the partial column sums)
+  const int64_t ws_floats = b->attn_ws ? me_attention_backward_workspace_floats(a->B, H, a->Ls, dh, a->max_seq) : 0;
+  if (launch_colsum_ws(b->g_h, dt, M, di, di, b->db1, b->attn_ws, ws_floats, st)) return 1;
   // dW1[di, d] = g_h^T . out1
   if (linear(dt, b->g_h, a->out1_T, b->dW1, di, d, M, di, d, d, 1, 1, true, 0, nullptr, nullptr, nullptr, 0, st))
     return 1;
@@ -182,7 +185,7 @@ extern "C" int me_layer_backward(const me_layer_bwd_args* b) {
   t.dq_acc = b->attn_ws;
   if (me_attention_backward(&t)) return 1;
 
-  if (launch_colsum(b->g_qkv, dt, M, 3 * d, 3 * d, b->dbqkv, st)) return 1;
+  if (launch_colsum_ws(b->g_qkv, dt, M, 3 * d, 3 * d, b->dbqkv, b->attn_ws, ws_floats, st)) return 1;
   // dWqkv[3d, d] = g_qkv^T . x
   if (linear(dt, b->g_qkv, a->x_T, b->dWqkv, 3 * d, d, M, 3 * d, d, d, 1, 1, true, 0, nullptr, nullptr, nullptr, 0,
              st))

@@ -51,6 +51,12 @@ timeit("column sums [M, d_inner] bf16", lambda: _lib.call("me_colsum", ptr(gh), 
 gq = torch.randn(M, 3 * d, device=dev, generator=g).to(torch.bfloat16)
 cq = torch.zeros(3 * d, device=dev)
 timeit("column sums [M, 3d] bf16", lambda: _lib.call("me_colsum", ptr(gq), ME_BF16, M, 3 * d, 3 * d, ptr(cq), st), M * 3 * d * 2)
+ws = torch.empty(148 * di, device=dev)
+timeit("column sums [M, d_inner] bf16, scratch", lambda: _lib.call("me_colsum_ws", ptr(gh), ME_BF16, M, di, di, ptr(cs), ptr(ws), ws.numel(), st), M * di * 2)
+timeit("column sums [M, 3d] bf16, scratch", lambda: _lib.call("me_colsum_ws", ptr(gq), ME_BF16, M, 3 * d, 3 * d, ptr(cq), ptr(ws), ws.numel(), st), M * 3 * d * 2)
+cs.zero_()
+_lib.call("me_colsum_ws", ptr(gh), ME_BF16, M, di, di, ptr(cs), ptr(ws), ws.numel(), st)
+print("scratch path max rel err vs torch:", float(((cs - gh.float().sum(0)).abs().max() / gh.float().sum(0).abs().max())))
 B, L = M // 1024, 1024
 tok = torch.randint(1, V, (B, L), device=dev, generator=g)
 cond = torch.rand(B, 2, device=dev, generator=g)
