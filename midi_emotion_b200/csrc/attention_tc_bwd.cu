@@ -613,39 +613,44 @@ __global__ void attn_bwd_prep_kernel(const bf16* __restrict__ out, const bf16* _
 // (both with the staging rows' chunk swizzle)
 __global__ void attn_bwd_finish_kernel(const float* __restrict__ dq_ws, bf16* __restrict__ dq, int64_t q_sb,
                                        int64_t q_si, int64_t q_sh, int B, int H, int L, int dh,
-                                       const float* __restrict__ dE_ws, float* __restrict__ dE, int max_seq) {
+                                       const float* __restrict__ dE_ws, float* __restrict__ dE, int max_seq,
+                                       int de_blocks) {
   const int q4 = dh / 4;
   const int swz = fb_swizzle_mask(dh);
-  const int64_t n_dq = static_cast<int64_t>(B) * H * L * q4;
-  const int64_t n_de = static_cast<int64_t>(max_seq) * q4;
-  for (int64_t t = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; t < n_dq + n_de;
-       t += static_cast<int64_t>(gridDim.x) * blockDim.x) {
-    if (t < n_dq) {
-      const int c = static_cast<int>(t % q4) * 4;
-      const int64_t row = t / q4;  // (b*H + h)*L + i
-      const int i = static_cast<int>(row % L);
-      const int64_t bh = row / L;
-      const int h = static_cast<int>(bh % H);
-      const int64_t b = bh / H;
-      const float4 v = *reinterpret_cast<const float4*>(dq_ws + row * dh + (((c >> 2) ^ (i & swz)) << 2));
-      __nv_bfloat162 lo = __floats2bfloat162_rn(v.x, v.y), hi = __floats2bfloat162_rn(v.z, v.w);
-      uint2 u;
-      u.x = *reinterpret_cast<uint32_t*>(&lo);
-      u.y = *reinterpret_cast<uint32_t*>(&hi);
-      *reinterpret_cast<uint2*>(dq + b * q_sb + i * q_si + h * q_sh + c) = u;
-    } else {
-      const int64_t u = t - n_dq;
+  if (static_cast<int>(blockIdx.x) < de_blocks) {
+    // the first blocks fold the private dE copies (32 independent loads per thread, issued together)
+    const int64_t n_de = static_cast<int64_t>(max_seq) * q4;
+    for (int64_t u = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; u < n_de;
+         u += static_cast<int64_t>(de_blocks) * blockDim.x) {
       const int c = static_cast<int>(u % q4) * 4;
       const int64_t e = u / q4;
+      const float* src = dE_ws + e * dh + (((c >> 2) ^ (static_cast<int>(e) & swz)) << 2);
+      float4 v[FB_DE_COPIES];
+#pragma unroll
+      for (int cp = 0; cp < FB_DE_COPIES; ++cp)
+        v[cp] = *reinterpret_cast<const float4*>(src + static_cast<int64_t>(cp) * max_seq * dh);
       float4 o = *reinterpret_cast<float4*>(dE + e * dh + c);
-      for (int cp = 0; cp < FB_DE_COPIES; ++cp) {
-        const float4 v =
-            *reinterpret_cast<const float4*>(dE_ws + (static_cast<int64_t>(cp) * max_seq + e) * dh +
-                                             (((c >> 2) ^ (static_cast<int>(e) & swz)) << 2));
-        o.x += v.x; o.y += v.y; o.z += v.z; o.w += v.w;
-      }
+#pragma unroll
+      for (int cp = 0; cp < FB_DE_COPIES; ++cp) { o.x += v[cp].x; o.y += v[cp].y; o.z += v[cp].z; o.w += v[cp].w; }
       *reinterpret_cast<float4*>(dE + e * dh + c) = o;
     }
+    return;
+  }
+  const int64_t n_dq = static_cast<int64_t>(B) * H * L * q4;
+  const int64_t stride = static_cast<int64_t>(gridDim.x - de_blocks) * blockDim.x;
+  for (int64_t t = static_cast<int64_t>(blockIdx.x - de_blocks) * blockDim.x + threadIdx.x; t < n_dq; t += stride) {
+    const int c = static_cast<int>(t % q4) * 4;
+    const int64_t row = t / q4;  // (b*H + h)*L + i
+    const int i = static_cast<int>(row % L);
+    const int64_t bh = row / L;
+    const int h = static_cast<int>(bh % H);
+    const int64_t b = bh / H;
+    const float4 v = *reinterpret_cast<const float4*>(dq_ws + row * dh + (((c >> 2) ^ (i & swz)) << 2));
+    __nv_bfloat162 lo = __floats2bfloat162_rn(v.x, v.y), hi = __floats2bfloat162_rn(v.z, v.w);
+    uint2 u;
+    u.x = *reinterpret_cast<uint32_t*>(&lo);
+    u.y = *reinterpret_cast<uint32_t*>(&hi);
+    *reinterpret_cast<uint2*>(dq + b * q_sb + i * q_si + h * q_sh + c) = u;
   }
 }
 
@@ -718,11 +723,12 @@ int launch_attn_bwd_tc(const me_attn_bwd_args* ba) {
   else rc = launch_bwd<32>(tq, tk, tv, tdo, te, p, grid, st);
   if (rc) return rc;
   {
-    const int64_t total = (static_cast<int64_t>(B) * H * L + a->max_seq) * (dh / 4);
+    const int64_t total = static_cast<int64_t>(B) * H * L * (dh / 4);
     const int64_t want = (total + 255) / 256;
-    const int blocks = static_cast<int>(want < 148 * 16 ? want : 148 * 16);
+    const int de_blocks = static_cast<int>((static_cast<int64_t>(a->max_seq) * (dh / 4) + 255) / 256);
+    const int blocks = static_cast<int>(want < 148 * 16 ? want : 148 * 16) + de_blocks;
     attn_bwd_finish_kernel<<<blocks, 256, 0, st>>>(p.dq_ws, static_cast<bf16*>(ba->dq), a->q_sb, a->q_si, a->q_sh, B, H,
-                                                   L, dh, p.dE_ws, ba->dE, a->max_seq);
+                                                   L, dh, p.dE_ws, ba->dE, a->max_seq, de_blocks);
     ME_LAUNCH_CHECK();
   }
   return 0;
