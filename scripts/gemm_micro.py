@@ -55,3 +55,10 @@ tot += run("wgrad out-proj", d, d, M, 1, 1, ME_F32, 0)
 tot += run("wgrad qkv", 3 * d, d, M, 1, 1, ME_F32, 0)
 print(f"layer total {tot * 1e3:.1f} us")
 run("head fwd", M, V, d, 0, 0, ME_BF16, B_)
+if os.environ.get("WHATIF"):
+    # what the dgrad GEMMs would cost with a pre-transposed (K-major) weight copy
+    run("dgrad ffn2 (mask), K-major W^T", M, di, d, 0, 0, ME_BF16, K_)
+    run("dgrad ffn1 (+res), K-major W^T", M, d, di, 0, 0, ME_F32, A_)
+    run("dgrad out-proj, K-major W^T", M, d, d, 0, 0, ME_BF16, 0)
+    run("dgrad qkv (+res), K-major W^T", M, d, 3 * d, 0, 0, ME_F32, A_)
+    run("dgrad ffn1 bf16 out no res, MN", M, d, di, 0, 1, ME_BF16, 0)
