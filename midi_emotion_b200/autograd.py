@@ -188,7 +188,8 @@ def run_backward(model, tokens, cond, a: _Acts, g_logits: torch.Tensor, ld_g: Op
     gh["fc.bias"].zero_()
     grads.update(gh)
     d_x = torch.empty(M, d, **f32)
-    _lib.call("me_colsum", ptr(g_logits), dtype, M, V, ld_g, ptr(grads["fc.bias"]), stream)
+    cs_ws = torch.empty(160 * V, **f32)     # partial rows of the column sums (no same-address atomics)
+    _lib.call("me_colsum_ws", ptr(g_logits), dtype, M, V, ld_g, ptr(grads["fc.bias"]), ptr(cs_ws), cs_ws.numel(), stream)
     if dtype == ME_BF16:
         _lib.call("me_gemm_bf16", ptr(g_logits), ptr(last["out2_T"]), ptr(grads["fc.weight"]), V, d, M, ld_g, d, d, 1, 1,
                   ME_F32, 0, None, None, None, 0, stream)

@@ -571,7 +571,7 @@ int launch_add_ln_bwd(const float* dout, const float* dout_add, const float* z, 
 // workspace; a second tiny kernel adds the partial rows into `out`.
 template <int NCH>
 __global__ void __launch_bounds__(256, 1)
-colsum_rows_kernel(const bf16* __restrict__ X, int M, int ldx, float* __restrict__ partial) {
+colsum_rows_kernel(const bf16* __restrict__ X, int M, int N, int ldx, float* __restrict__ partial) {
   __shared__ float fold[NCH * 256];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int64_t warp0 = static_cast<int64_t>(blockIdx.x) * 8 + warp;
@@ -588,8 +588,10 @@ colsum_rows_kernel(const bf16* __restrict__ X, int M, int ldx, float* __restrict
     uint4 u0[NCH], u1[NCH];
 #pragma unroll
     for (int k = 0; k < NCH; ++k) {
-      u0[k] = *reinterpret_cast<const uint4*>(p0 + 256 * k);
-      u1[k] = *reinterpret_cast<const uint4*>(p1 + 256 * k);
+      // chunks past the row pitch are redirected to chunk 0 (branch-free loads); their sums are never written
+      const int off = (256 * k + lane * 8 + 8 <= ldx) ? 256 * k : -lane * 8;
+      u0[k] = *reinterpret_cast<const uint4*>(p0 + off);
+      u1[k] = *reinterpret_cast<const uint4*>(p1 + off);
     }
     const float w1 = two ? 1.f : 0.f;
 #pragma unroll
@@ -616,15 +618,19 @@ colsum_rows_kernel(const bf16* __restrict__ X, int M, int ldx, float* __restrict
     }
     __syncthreads();
   }
-  float* prow = partial + static_cast<int64_t>(blockIdx.x) * (NCH * 256);
-  for (int c = threadIdx.x; c < NCH * 256; c += 256) prow[c] = fold[c];
+  float* prow = partial + static_cast<int64_t>(blockIdx.x) * N;
+  for (int c = threadIdx.x; c < N; c += 256) prow[c] = fold[c];
 }
+// out[n] += sum of the partial rows; blockIdx.y splits the rows (a handful of adds per column, not hundreds)
 __global__ void colsum_finish_kernel(const float* __restrict__ partial, int rows, int N, float* __restrict__ out) {
   const int n = blockIdx.x * blockDim.x + threadIdx.x;
   if (n >= N) return;
+  const int per = (rows + gridDim.y - 1) / gridDim.y;
+  const int r0 = blockIdx.y * per, r1 = min(rows, r0 + per);
   float s = 0.f;
-  for (int r = 0; r < rows; ++r) s += partial[static_cast<int64_t>(r) * N + n];
-  out[n] += s;
+#pragma unroll 8
+  for (int r = r0; r < r1; ++r) s += partial[static_cast<int64_t>(r) * N + n];
+  if (r1 > r0) atomicAdd(&out[n], s);
 }
 
 int launch_colsum(const void* X, int dtype, int M, int N, int ldx, float* out, cudaStream_t st) {
@@ -648,16 +654,16 @@ int launch_colsum(const void* X, int dtype, int M, int N, int ldx, float* out, c
 int launch_colsum_ws(const void* X, int dtype, int M, int N, int ldx, float* out, float* ws, int64_t ws_floats,
                      cudaStream_t st) {
   const int blocks = sm_count();
-  if (ws && ws_floats >= static_cast<int64_t>(blocks) * N && dtype == ME_BF16 && N % 256 == 0 && N <= 3072 &&
-      ldx % 8 == 0 && (reinterpret_cast<uintptr_t>(X) & 15) == 0 && M >= 2048) {
+  if (ws && ws_floats >= static_cast<int64_t>(blocks) * N && dtype == ME_BF16 && N <= 3072 && ldx % 8 == 0 &&
+      (reinterpret_cast<uintptr_t>(X) & 15) == 0 && (reinterpret_cast<uintptr_t>(ws) & 15) == 0 && M >= 2048) {
     const bf16* x = static_cast<const bf16*>(X);
-    switch (N / 256) {
-#define ME_CS(NC) case NC: colsum_rows_kernel<NC><<<blocks, 256, 0, st>>>(x, M, ldx, ws); break;
+    switch ((N + 255) / 256) {
+#define ME_CS(NC) case NC: colsum_rows_kernel<NC><<<blocks, 256, 0, st>>>(x, M, N, ldx, ws); break;
       ME_CS(1) ME_CS(2) ME_CS(3) ME_CS(4) ME_CS(5) ME_CS(6) ME_CS(7) ME_CS(8) ME_CS(9) ME_CS(10) ME_CS(11) ME_CS(12)
 #undef ME_CS
     }
     ME_LAUNCH_CHECK();
-    colsum_finish_kernel<<<(N + 255) / 256, 256, 0, st>>>(ws, blocks, N, out);
+    colsum_finish_kernel<<<dim3((N + 255) / 256, 8), 256, 0, st>>>(ws, blocks, N, out);
     ME_LAUNCH_CHECK();
     return 0;
   }
