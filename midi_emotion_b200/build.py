@@ -22,6 +22,8 @@ NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr", "-I", INCLUDE,
 ]
+if os.environ.get("ME_TRACE") == "1":   # per-phase clock stamps in the attention backward kernel (tuning builds)
+    NVCC_FLAGS.append("-DME_ATTN_BWD_TRACE")
 
 
 def _nvcc() -> str:

@@ -67,11 +67,16 @@ struct FbParams {
   long long* trace;  // debugging: per-phase clock64() stamps of one CTA (me_debug_trace_set), else NULL
 };
 static long long* g_attn_bwd_trace = nullptr;
-// stamps: [role (0 = warp 0, 1 = warp 7, 2 = control warp)][step < 16][event < 16]
+// stamps: [role (0 = warp 0, 1 = warp 7, 2 = control warp)][step < 16][event < 16].  Compiled in only with
+// -DME_ATTN_BWD_TRACE (ME_TRACE=1 python -m midi_emotion_b200.build): the predicated stamps cost registers.
+#ifdef ME_ATTN_BWD_TRACE
 #define FB_TRACE(role, st, k)                                                                  \
   do {                                                                                         \
     if (tr && (st) < 16) p.trace[((role) * 16 + (st)) * 16 + (k)] = clock64();                 \
   } while (0)
+#else
+#define FB_TRACE(role, st, k) do { } while (0)
+#endif
 
 // TMEM -> shared staging: NCOLS (multiple of 8) accumulator columns of this thread's lane
 template <int NCOLS>
