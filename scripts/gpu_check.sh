@@ -9,3 +9,5 @@ run attn_tc tests/test_gpu_kernels.py -k "tensor_core"
 run model_fp32 tests/test_gpu_model.py -k "not bf16"
 run model_bf16 tests/test_gpu_model.py -k "bf16"
 run decode tests/test_gpu_decode.py
+run fullsize tests/test_gpu_fullsize.py
+run sampling_loss tests/test_gpu_sampling.py tests/test_gpu_loss.py
