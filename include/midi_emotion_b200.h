@@ -248,6 +248,13 @@ typedef struct me_layer_bwd_args {
   void* g_o;            /* T [M, d]   */
   float* dsum;          /* [B, H, Ls] */
   float* attn_ws;       /* me_attention_backward_workspace_floats(...) floats; ME_ATTN_TENSOR only */
+  /* Optional (ME_BF16 only), the gradient as a sum of an fp32 and a compute-type part -- the rounding points of
+   * the reference under autocast (a Linear's input gradient is bf16, the residual add is fp32):
+   *   d_out_T  in : T [M, d] or NULL; the gradient w.r.t. the layer output is d_out + d_out_T
+   *   d_x_T    out: T [M, d] or NULL; when given, the gradient w.r.t. the layer input is d_x + d_x_T
+   *                 (d_x_T = the QKV projection's input gradient straight out of its GEMM) */
+  const void* d_out_T;
+  void* d_x_T;
 } me_layer_bwd_args;
 int me_layer_backward(const me_layer_bwd_args* a);
 

@@ -65,7 +65,8 @@ class LayerArgs(C.Structure):
 
 
 _LAYER_BWD_PTRS = ["d_out", "d_x", "dWqkv", "dbqkv", "dE", "dWo", "dbo", "dln1_w", "dln1_b", "dW1", "db1", "dW2",
-                   "db2", "dln2_w", "dln2_b", "g_a", "g_b", "g_T", "g_h", "g_qkv", "g_o", "dsum", "attn_ws"]
+                   "db2", "dln2_w", "dln2_b", "g_a", "g_b", "g_T", "g_h", "g_qkv", "g_o", "dsum", "attn_ws",
+                   "d_out_T", "d_x_T"]
 
 
 class LayerBwdArgs(C.Structure):

@@ -212,6 +212,11 @@ def run_backward(model, tokens, cond, a: _Acts, g_logits: torch.Tensor, ld_g: Op
     if a.attn_impl == _lib.ATTN_TENSOR:
         n_ws = _lib.load().me_attention_backward_workspace_floats(B, H, Ls, dh, model.max_seq)
         ws["attn_ws"] = torch.empty(n_ws, **f32)
+    # bf16 path: the layer-input gradient travels as (fp32 residual part, bf16 sub-layer part); the parts are
+    # added by the next LayerNorm backward (me_layer_bwd_args.d_out_T / d_x_T)
+    split = dtype == ME_BF16
+    d_parts = [torch.empty(M, d, **tt), torch.empty(M, d, **tt)] if split else None
+    d_in_T = None
     for l in range(model.num_layer - 1, -1, -1):
         lay = model.enc_layers[l]
         act = a.layers[l]
@@ -231,7 +236,12 @@ def run_backward(model, tokens, cond, a: _Acts, g_logits: torch.Tensor, ld_g: Op
             setattr(ba, k, ptr(t))
         for k in ("g_a", "g_b", "g_T", "g_h", "g_qkv", "g_o", "dsum", "attn_ws"):
             setattr(ba, k, ptr(ws[k]))
+        if split:
+            d_next_T = d_parts[l & 1]
+            ba.d_out_T, ba.d_x_T = ptr(d_in_T), ptr(d_next_T)
         _lib.call("me_layer_backward", C.byref(ba))
+        if split:
+            d_in_T = d_next_T
         for i, n in enumerate(("Wq", "Wk", "Wv")):
             grads[pre + f"rga.{n}.weight"] = dWqkv[i * d:(i + 1) * d]
             grads[pre + f"rga.{n}.bias"] = dbqkv[i * d:(i + 1) * d]
@@ -245,6 +255,8 @@ def run_backward(model, tokens, cond, a: _Acts, g_logits: torch.Tensor, ld_g: Op
         if hook is not None:
             hook(flat_l)
 
+    if split and d_in_T is not None:
+        d_x.add_(d_in_T)     # the input stage takes the whole gradient in fp32
     # input stage
     cw0, cb0, cw1, cb1 = model._cond_params()
     shapes = {"emb": tuple(model.embedding.weight.shape)}

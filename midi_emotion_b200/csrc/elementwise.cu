@@ -266,7 +266,8 @@ add_ln_fwd_kernel(const float* __restrict__ x_res, const T* __restrict__ y, cons
 // flushed with one atomicAdd per column per block.
 template <typename T, int NCH>
 __global__ void __launch_bounds__(LN_THREADS)
-add_ln_bwd_kernel(const float* __restrict__ dout, const float* __restrict__ dout_add, const float* __restrict__ z,
+add_ln_bwd_kernel(const float* __restrict__ dout, const float* __restrict__ dout_add,
+                  const bf16* __restrict__ dout_add_T, const float* __restrict__ z,
                   const float* __restrict__ mean, const float* __restrict__ rstd, const float* __restrict__ gamma,
                   int M, int d, float p, uint64_t seed, float* __restrict__ dz_f32, T* __restrict__ dy_T,
                   float* __restrict__ d_gamma, float* __restrict__ d_beta, float* __restrict__ d_ybias) {
@@ -301,6 +302,16 @@ add_ln_bwd_kernel(const float* __restrict__ dout, const float* __restrict__ dout
         const int c = 4 * (lane + 32 * k);
         float t[4];
         Vec4<float>::load(dout_add + row * d + (c < d ? c : 0), t);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) dy[k][e] += t[e];
+      }
+    }
+    if (dout_add_T) {   // the sub-layer's input gradient in the compute type (a bf16 GEMM output, as autocast has it)
+#pragma unroll
+      for (int k = 0; k < NCH; ++k) {
+        const int c = 4 * (lane + 32 * k);
+        float t[4];
+        Vec4<bf16>::load(dout_add_T + row * d + (c < d ? c : 0), t);
 #pragma unroll
         for (int e = 0; e < 4; ++e) dy[k][e] += t[e];
       }
@@ -518,7 +529,8 @@ int launch_add_ln_fwd(const float* x_res, const void* y, int dtype, const float*
 
 template <typename T>
 static int ln_bwd_dispatch(int nch, int blocks, size_t smem, cudaStream_t st, const float* dout,
-                           const float* dout_add, const float* z, const float* mean, const float* rstd,
+                           const float* dout_add, const bf16* dout_add_T, const float* z, const float* mean,
+                           const float* rstd,
                            const float* gamma, int M, int d, float p, uint64_t seed, float* dz_f32, T* dy_T,
                            float* d_gamma, float* d_beta, float* d_ybias) {
 #define ME_LN_BWD(N)                                                                                             \
@@ -528,8 +540,8 @@ static int ln_bwd_dispatch(int nch, int blocks, size_t smem, cudaStream_t st, co
       ME_CUDA(cudaFuncSetAttribute(add_ln_bwd_kernel<T, N>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); \
       configured = true;                                                                                         \
     }                                                                                                            \
-    add_ln_bwd_kernel<T, N><<<blocks, LN_THREADS, smem, st>>>(dout, dout_add, z, mean, rstd, gamma, M, d, p, seed, \
-                                                              dz_f32, dy_T, d_gamma, d_beta, d_ybias);            \
+    add_ln_bwd_kernel<T, N><<<blocks, LN_THREADS, smem, st>>>(dout, dout_add, dout_add_T, z, mean, rstd, gamma, M, d, \
+                                                              p, seed, dz_f32, dy_T, d_gamma, d_beta, d_ybias);   \
   } while (0)
   switch (nch) {
     case 1: ME_LN_BWD(1); break;
@@ -544,9 +556,10 @@ static int ln_bwd_dispatch(int nch, int blocks, size_t smem, cudaStream_t st, co
   return 0;
 }
 
-int launch_add_ln_bwd(const float* dout, const float* dout_add, const float* z, const float* mean,
-                      const float* rstd, const float* gamma, int M, int d, float p, uint64_t seed, int dtype,
-                      float* dz_f32, void* dy_T, float* d_gamma, float* d_beta, float* d_ybias, cudaStream_t st) {
+int launch_add_ln_bwd(const float* dout, const float* dout_add, const void* dout_add_T, const float* z,
+                      const float* mean, const float* rstd, const float* gamma, int M, int d, float p, uint64_t seed,
+                      int dtype, float* dz_f32, void* dy_T, float* d_gamma, float* d_beta, float* d_ybias,
+                      cudaStream_t st) {
   ME_CHECK(d % 4 == 0 && d <= 1024, "layernorm backward: d=%d must be a multiple of 4 and <= 1024", d);
   const int wpb = LN_THREADS / 32;
   int blocks = (M + wpb - 1) / wpb;
@@ -554,11 +567,11 @@ int launch_add_ln_bwd(const float* dout, const float* dout_add, const float* z, 
   if (blocks > cap) blocks = cap;
   const size_t smem = (1 + 3 * (LN_THREADS / 32)) * static_cast<size_t>(d) * sizeof(float);
   if (dtype == ME_BF16)
-    ln_bwd_dispatch<bf16>(ln_nch(d), blocks, smem, st, dout, dout_add, z, mean, rstd, gamma, M, d, p, seed, dz_f32,
-                          static_cast<bf16*>(dy_T), d_gamma, d_beta, d_ybias);
+    ln_bwd_dispatch<bf16>(ln_nch(d), blocks, smem, st, dout, dout_add, static_cast<const bf16*>(dout_add_T), z, mean, rstd,
+                          gamma, M, d, p, seed, dz_f32, static_cast<bf16*>(dy_T), d_gamma, d_beta, d_ybias);
   else
-    ln_bwd_dispatch<float>(ln_nch(d), blocks, smem, st, dout, dout_add, z, mean, rstd, gamma, M, d, p, seed, dz_f32,
-                           static_cast<float*>(dy_T), d_gamma, d_beta, d_ybias);
+    ln_bwd_dispatch<float>(ln_nch(d), blocks, smem, st, dout, dout_add, nullptr, z, mean, rstd, gamma, M, d, p, seed,
+                           dz_f32, static_cast<float*>(dy_T), d_gamma, d_beta, d_ybias);
   ME_LAUNCH_CHECK();
   return 0;
 }
@@ -723,7 +736,7 @@ extern "C" int me_add_layernorm_backward(const float* dout, const float* dout_ad
                                          float dropout_p, uint64_t seed, int dtype, float* dz_f32, void* dy_T,
                                          float* d_gamma, float* d_beta, void* stream) {
   ME_CHECK(M > 0 && d > 0 && d <= 1024, "me_add_layernorm_backward: bad dims");
-  return launch_add_ln_bwd(dout, dout_add, z, mean, rstd, gamma, M, d, dropout_p, seed, dtype, dz_f32, dy_T,
+  return launch_add_ln_bwd(dout, dout_add, nullptr, z, mean, rstd, gamma, M, d, dropout_p, seed, dtype, dz_f32, dy_T,
                            d_gamma, d_beta, nullptr, static_cast<cudaStream_t>(stream));
 }
 

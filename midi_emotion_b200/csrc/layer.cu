@@ -14,9 +14,10 @@ int launch_gemm_f32(const float* A, const float* B, float* D, int M, int N, int 
 int launch_add_ln_fwd(const float* x_res, const void* y, int dtype, const float* gamma, const float* beta,
                       float eps, int M, int d, float p, uint64_t seed, float* out_f32, void* out_T, float* z,
                       float* mean, float* rstd, cudaStream_t st);
-int launch_add_ln_bwd(const float* dout, const float* dout_add, const float* z, const float* mean,
-                      const float* rstd, const float* gamma, int M, int d, float p, uint64_t seed, int dtype,
-                      float* dz_f32, void* dy_T, float* d_gamma, float* d_beta, float* d_ybias, cudaStream_t st);
+int launch_add_ln_bwd(const float* dout, const float* dout_add, const void* dout_add_T, const float* z,
+                      const float* mean, const float* rstd, const float* gamma, int M, int d, float p, uint64_t seed,
+                      int dtype, float* dz_f32, void* dy_T, float* d_gamma, float* d_beta, float* d_ybias,
+                      cudaStream_t st);
 int launch_colsum_ws(const void* X, int dtype, int M, int N, int ldx, float* out, float* ws, int64_t ws_floats,
                      cudaStream_t st);
 int launch_kv_write(const void* qkv, int dtype, int B, int Ls, int H, int dh, void* kc, void* vc, int T_max,
@@ -145,8 +146,12 @@ extern "C" int me_layer_backward(const me_layer_bwd_args* b) {
   ME_CUDA(cudaMemsetAsync(b->dE, 0, static_cast<size_t>(a->max_seq) * dh * sizeof(float), st));
 
   // ---- FFN block: out2 = LN2(out1 + drop(W2 relu(W1 out1 + b1) + b2))
-  if (launch_add_ln_bwd(b->d_out, nullptr, a->z2, a->mean2, a->rstd2, a->ln2_w, M, d, p, s2, dt, b->g_a, b->g_T,
-                        b->dln2_w, b->dln2_b, b->db2, st))  // db2 = column sums of the masked gradient
+  // bf16 path: the input gradients of the two sub-layers leave their GEMMs in bf16 (the fast TMA-store
+  // epilogue; the same rounding point as the reference under autocast) and the following LayerNorm backward
+  // adds them to the fp32 residual-stream gradient itself -- no fp32 [M, d] round trip through the GEMM epilogue.
+  const bool split = dt == ME_BF16 && b->d_x_T != nullptr;
+  if (launch_add_ln_bwd(b->d_out, nullptr, dt == ME_BF16 ? b->d_out_T : nullptr, a->z2, a->mean2, a->rstd2, a->ln2_w, M, d,
+                        p, s2, dt, b->g_a, b->g_T, b->dln2_w, b->dln2_b, b->db2, st))  // db2 = column sums of the masked gradient
     return 1;
   // dW2[d, di] = g_T^T . h
   if (linear(dt, b->g_T, a->h, b->dW2, d, di, M, d, di, di, 1, 1, true, 0, nullptr, nullptr, nullptr, 0, st)) return 1;
@@ -160,15 +165,23 @@ extern "C" int me_layer_backward(const me_layer_bwd_args* b) {
   // dW1[di, d] = g_h^T . out1
   if (linear(dt, b->g_h, a->out1_T, b->dW1, di, d, M, di, d, d, 1, 1, true, 0, nullptr, nullptr, nullptr, 0, st))
     return 1;
-  // g_b[M, d] = g_h . W1 + g_a   (total gradient w.r.t. out1, fp32)
-  if (linear(dt, b->g_h, a->W1, b->g_b, M, d, di, di, d, d, 0, 1, true, ME_EPI_ADD_F32, nullptr, b->g_a, nullptr, 0,
-             st))
-    return 1;
-
-  // ---- attention block: out1 = LN1(x + drop(Wo attn + bo))
-  if (launch_add_ln_bwd(b->g_b, nullptr, a->z1, a->mean1, a->rstd1, a->ln1_w, M, d, p, s1, dt, b->g_a, b->g_T,
-                        b->dln1_w, b->dln1_b, b->dbo, st))
-    return 1;
+  if (split) {
+    // g_o (free until the out-projection dgrad) <- g_h . W1 in bf16; LN1 backward reads g_a + g_o and writes the
+    // fp32 part of d_x directly
+    if (linear(dt, b->g_h, a->W1, b->g_o, M, d, di, di, d, d, 0, 1, false, 0, nullptr, nullptr, nullptr, 0, st)) return 1;
+    if (launch_add_ln_bwd(b->g_a, nullptr, b->g_o, a->z1, a->mean1, a->rstd1, a->ln1_w, M, d, p, s1, dt, b->d_x, b->g_T,
+                          b->dln1_w, b->dln1_b, b->dbo, st))
+      return 1;
+  } else {
+    // g_b[M, d] = g_h . W1 + g_a   (total gradient w.r.t. out1, fp32)
+    if (linear(dt, b->g_h, a->W1, b->g_b, M, d, di, di, d, d, 0, 1, true, ME_EPI_ADD_F32, nullptr, b->g_a, nullptr, 0,
+               st))
+      return 1;
+    // ---- attention block: out1 = LN1(x + drop(Wo attn + bo))
+    if (launch_add_ln_bwd(b->g_b, nullptr, nullptr, a->z1, a->mean1, a->rstd1, a->ln1_w, M, d, p, s1, dt, b->g_a, b->g_T,
+                          b->dln1_w, b->dln1_b, b->dbo, st))
+      return 1;
+  }
   if (linear(dt, b->g_T, a->attn_o, b->dWo, d, d, M, d, d, d, 1, 1, true, 0, nullptr, nullptr, nullptr, 0, st))
     return 1;
   if (linear(dt, b->g_T, a->Wo, b->g_o, M, d, d, d, d, d, 0, 1, false, 0, nullptr, nullptr, nullptr, 0, st)) return 1;
@@ -190,10 +203,16 @@ extern "C" int me_layer_backward(const me_layer_bwd_args* b) {
   if (linear(dt, b->g_qkv, a->x_T, b->dWqkv, 3 * d, d, M, 3 * d, d, d, 1, 1, true, 0, nullptr, nullptr, nullptr, 0,
              st))
     return 1;
-  // d_x[M, d] = g_qkv . Wqkv + g_a
-  if (linear(dt, b->g_qkv, a->Wqkv, b->d_x, M, d, 3 * d, 3 * d, d, d, 0, 1, true, ME_EPI_ADD_F32, nullptr, b->g_a,
-             nullptr, 0, st))
-    return 1;
+  if (split) {
+    // d_x = (fp32 part, written by LN1 backward above) + d_x_T, with d_x_T = g_qkv . Wqkv in bf16
+    if (linear(dt, b->g_qkv, a->Wqkv, b->d_x_T, M, d, 3 * d, 3 * d, d, d, 0, 1, false, 0, nullptr, nullptr, nullptr, 0, st))
+      return 1;
+  } else {
+    // d_x[M, d] = g_qkv . Wqkv + g_a
+    if (linear(dt, b->g_qkv, a->Wqkv, b->d_x, M, d, 3 * d, 3 * d, d, d, 0, 1, true, ME_EPI_ADD_F32, nullptr, b->g_a,
+               nullptr, 0, st))
+      return 1;
+  }
   return 0;
 }
 
