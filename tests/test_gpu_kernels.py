@@ -471,3 +471,36 @@ def test_gemm_tcgen05_cta_pair_staged_store_ragged(M, N, K, b_mn):
     if ldd != N:
         pad = got[:, N:].float()                          # pad columns: untouched (NaN fill) or written as zero
         assert (torch.isnan(pad) | (pad == 0)).all()
+
+
+# ---------------------------------------------------------------------------------------------
+# column sums with scratch (no same-address atomics) and the batched weight-copy refresh
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("M,N,ld", [(4096, 256, 256), (2048, 1007, 1008), (5000, 2304, 2304), (3000, 3072, 3080),
+                                    (100, 512, 512)])
+def test_colsum_with_scratch_matches_torch(M, N, ld):
+    g = torch.Generator(device="cuda").manual_seed(M + N)
+    X = torch.randn(M, ld, device="cuda", generator=g).to(torch.bfloat16)
+    out = torch.full((N,), 0.5, device="cuda")
+    ws = torch.empty(160 * N, device="cuda")
+    _lib.call("me_colsum_ws", ptr(X), ME_BF16, M, N, ld, ptr(out), ptr(ws), ws.numel(), stream())
+    want = X[:, :N].float().sum(0) + 0.5          # accumulates into `out`
+    assert torch.allclose(out, want, rtol=1e-4, atol=1e-2)
+
+
+def test_convert_batched_matches_convert_2d():
+    import ctypes as C
+    srcs = [torch.randn(33, 40, device="cuda"), torch.randn(7, 64, device="cuda"), torch.randn(1, 100, device="cuda"),
+            torch.randn(16, 24, device="cuda").to(torch.bfloat16)]
+    dsts = [torch.empty(33, 40, device="cuda", dtype=torch.bfloat16), torch.empty(7, 72, device="cuda", dtype=torch.bfloat16),
+            torch.empty(1, 100, device="cuda"), torch.empty(16, 24, device="cuda")]
+    code = {torch.float32: ME_F32, torch.bfloat16: ME_BF16}
+    table = (_lib.ConvertDesc * len(srcs))(*[
+        _lib.ConvertDesc(s.data_ptr(), d.data_ptr(), s.shape[0], s.shape[1], s.stride(0), d.stride(0), code[s.dtype], code[d.dtype])
+        for s, d in zip(srcs, dsts)])
+    dev_table = torch.frombuffer(bytearray(bytes(table)), dtype=torch.uint8).cuda()
+    _lib.call("me_convert_batched", ptr(dev_table), len(srcs), stream())
+    for s, d in zip(srcs, dsts):
+        cols = s.shape[1]
+        assert torch.equal(d[:, :cols], s.to(d.dtype))
+        assert (d[:, cols:] == 0).all()               # pad columns are zeroed
