@@ -60,9 +60,19 @@ __device__ __forceinline__ void gemm_epilogue_chunk(const GemmParams& p, const u
   gemm_epilogue_math<CW>(p, r, bs, addv, maskw, use_bias, do_add, do_mask, v);
   if (p.splits > 1) {
     float* dp = static_cast<float*>(p.D) + static_cast<int64_t>(m) * p.ldd + nb;
+    if (full && (p.ldd % 4 == 0)) {
+      // 16-byte vector reductions: a quarter of the instructions of scalar atomics (the split-K epilogue of the
+      // weight-gradient GEMMs spent ~20 us per launch issuing 32768 scalar atomics per CTA)
 #pragma unroll
-    for (int j = 0; j < CW; ++j)
-      if (nb + j < p.N) atomicAdd(dp + j, v[j]);
+      for (int j = 0; j < CW; j += 4)
+        asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dp + j), "f"(v[j]), "f"(v[j + 1]), "f"(v[j + 2]),
+                     "f"(v[j + 3])
+                     : "memory");
+    } else {
+#pragma unroll
+      for (int j = 0; j < CW; ++j)
+        if (nb + j < p.N) atomicAdd(dp + j, v[j]);
+    }
   } else if (p.out_dtype == ME_BF16) {
     bf16* dp = static_cast<bf16*>(p.D) + static_cast<int64_t>(m) * p.ldd + nb;
     if (vec_ok && full) {
