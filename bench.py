@@ -29,6 +29,27 @@ CFG2 = dict(vocab_size=1007, n_layer=12, n_head=12, d_model=768, d_inner=3072, d
 SEQ_LEN = 1024
 BATCH_PER_GPU = 32
 METRIC = "MIDI tokens/sec train fwd+bwd @ seq1024"
+CFG3 = dict(vocab_size=1007, n_layer=24, n_head=16, d_model=1024, d_inner=4096, dropout=0.1, d_condition=192,
+            conditioning="continuous_concat")
+
+
+def workload(name):
+    """BASELINE.json configs -> (model config, token length L, stack length Ls, sequences per GPU, metric, label).
+    `cfg2` is the configuration the metric is quoted on; the others are extra lines."""
+    if name == "cfg2":
+        return dict(CFG2), SEQ_LEN, SEQ_LEN, BATCH_PER_GPU, METRIC, "continuous_concat 12L/768d/12h seq1024 " \
+            "batch32/GPU bf16 (BASELINE configs[1])"
+    if name == "cfg3":
+        return dict(CFG3), 2048, 2048, 16, "MIDI tokens/sec train fwd+bwd @ seq2048", \
+            "continuous_concat 24L/1024d/16h seq2048 batch16/GPU bf16 (BASELINE configs[2])"
+    mode = name
+    cfg = dict(CFG2, conditioning=mode, d_condition=-1)
+    if mode == "discrete_token":       # ten emotion tokens appended to the vocabulary (loader.py:58-75)
+        cfg["vocab_size"] = 1017
+    # continuous_token prepends two condition positions (music_continuous_token.py:93-100; loader.py:55-57 shortens
+    # the token window by two), so the stack still runs at 1024 positions
+    L = SEQ_LEN - 2 if mode == "continuous_token" else SEQ_LEN
+    return cfg, L, SEQ_LEN, BATCH_PER_GPU, METRIC, f"{mode} 12L/768d/12h seq1024 batch32/GPU bf16 (BASELINE configs[4] sweep)"
 
 
 def flops_per_token(cfg, Ls):
@@ -98,12 +119,22 @@ class ClockSampler:
 
 
 def synthetic_batch(cfg, B, L, seed, device=None, pin=False):
-    """Tokens ~ U{1..V-1}, <START>=1 first, no padding; target = next token; VA ~ U(-1,1)."""
+    """Tokens ~ U{1..1006}, <START>=1 first, no padding; target = next token; VA ~ U(-1,1).
+    discrete_token: an emotion token (ids 1007..1016) leads the sequence and the condition is NaN
+    (loader.py:58-75,185-187); none: NaN condition; continuous_token: target left-padded by two pads
+    (loader.py:55-57: the two prepended condition positions predict nothing)."""
     g = torch.Generator().manual_seed(seed)
-    seq = torch.randint(1, cfg["vocab_size"], (B, L + 1), generator=g)
+    mode = cfg["conditioning"]
+    seq = torch.randint(1, 1007, (B, L + 1), generator=g)
     seq[:, 0] = 1
+    if mode == "discrete_token":
+        seq[:, 0] = torch.randint(1007, 1017, (B,), generator=g)
     tokens, target = seq[:, :-1].contiguous(), seq[:, 1:].contiguous()
     cond = torch.rand(B, 2, generator=g) * 2 - 1
+    if mode in ("none", "discrete_token"):
+        cond = torch.full_like(cond, float("nan"))
+    if mode == "continuous_token":
+        target = torch.cat([torch.zeros(B, 2, dtype=target.dtype), target], 1).contiguous()
     if pin:
         tokens, target, cond = tokens.pin_memory(), target.pin_memory(), cond.pin_memory()
     if device is not None:
@@ -114,11 +145,11 @@ def synthetic_batch(cfg, B, L, seed, device=None, pin=False):
 # ----------------------------------------------------------------------------------------------
 # reference arm: the reference algorithm (oracle port) on the host cores
 # ----------------------------------------------------------------------------------------------
-def cpu_train_tokens_per_s(steps, warmup, B=1, L=SEQ_LEN, threads=None):
+def cpu_train_tokens_per_s(steps, warmup, B=1, L=SEQ_LEN, threads=None, cfg=None):
     from oracle import midi_oracle as O
     threads = threads or os.cpu_count() or 1
     torch.set_num_threads(threads)
-    cfg = dict(CFG2, dropout=0.0)
+    cfg = dict(cfg or CFG2, dropout=0.0)
     params = O.init_params(cfg, seed=1234, e_scale=0.2)
     tokens, cond, target = synthetic_batch(cfg, B, L, 1002)
     state = {}
@@ -130,22 +161,23 @@ def cpu_train_tokens_per_s(steps, warmup, B=1, L=SEQ_LEN, threads=None):
         if i >= warmup:
             times.append(dt)
     total = sum(times)
-    return B * L * len(times) / total, 1e3 * total / len(times), threads
+    return B * target.size(1) * len(times) / total, 1e3 * total / len(times), threads
 
 
 def run_reference(args, rank):
     if rank != 0:
         return
     steps, warmup = max(1, args.steps), max(0, args.warmup)
+    cfg, L, Ls, _, metric, label = workload(args.workload)
     # bounded sample: B=1 sequence of the same model/seq_len per step (the full batch of 32 is ~2 min/step)
-    tps, ms, threads = cpu_train_tokens_per_s(steps, warmup, B=1)
-    sample = f"{steps} steps of batch 1 x seq {SEQ_LEN} (same model, fp32, fwd+CE+bwd+clip+Adam), {threads} threads"
+    tps, ms, threads = cpu_train_tokens_per_s(steps, warmup, B=1, L=L, cfg=cfg)
+    sample = f"{steps} steps of batch 1 x seq {Ls} (same model, fp32, fwd+CE+bwd+clip+Adam), {threads} threads"
     line = {
-        "impl": "reference", "metric": METRIC, "value": tps, "unit": "tokens/s", "n_gpus": args.gpus, "steps": steps,
+        "impl": "reference", "metric": metric, "value": tps, "unit": "tokens/s", "n_gpus": args.gpus, "steps": steps,
         "warmup": warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "train step continuous_concat 12L/768d/12h seq1024 (configs[1])",
-                   "global_batch": 1, "seq_len": SEQ_LEN, "note": "oracle port of the reference PyTorch path on CPU"},
+        "config": {"workload": "train step (fwd+CE+bwd+clip+Adam) " + label,
+                   "global_batch": 1, "seq_len": Ls, "note": "oracle port of the reference PyTorch path on CPU"},
         "cpu_baseline": {"value": tps, "unit": "tokens/s", "cores": threads, "kind": "port", "sample": sample},
         "e2e": {"value": tps, "unit": "tokens/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -212,7 +244,11 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--batch", type=int, default=BATCH_PER_GPU, help="sequences per GPU")
+    ap.add_argument("--workload", default="cfg2",
+                    choices=["cfg2", "cfg3", "discrete_token", "continuous_token", "continuous_concat", "none"],
+                    help="cfg2 = BASELINE configs[1] (the quoted metric); cfg3 = configs[2]; a conditioning mode = "
+                         "that row of the configs[4] sweep")
+    ap.add_argument("--batch", type=int, default=None, help="sequences per GPU (default: the workload's)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--attn", default="auto", choices=["auto", "simt", "tensor"])
     ap.add_argument("--no-decode", action="store_true", help="skip the KV-cache decode measurement (configs[3])")
@@ -238,10 +274,13 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
     lib = _lib.load()
     W, K = max(3, args.warmup), max(1, args.steps)
-    B, L = args.batch, SEQ_LEN
+    if args.workload == "continuous_concat":
+        args.workload = "cfg2"
+    CFG, L, Ls, B, metric, label = workload(args.workload)
+    B = args.batch or B
 
     torch.manual_seed(1234)
-    model, _ = build_model(dict(CFG2))
+    model, _ = build_model(dict(CFG))
     with torch.no_grad():
         for n, p in model.named_parameters():
             if n.endswith("rga.E"):
@@ -251,7 +290,7 @@ def main():
     ddp = DataParallel(model)
     opt = torch.optim.Adam(model.parameters(), lr=2e-5, fused=True)
 
-    host = [synthetic_batch(CFG2, B, L, 1002 + 17 * rank + i, pin=True) for i in range(2)]
+    host = [synthetic_batch(CFG, B, L, 1002 + 17 * rank + i, pin=True) for i in range(2)]
     resident = [tuple(t.to(dev) for t in h) for h in host]
 
     def train_step(tokens, cond, target):
@@ -281,7 +320,7 @@ def main():
     # ---- timed region 1: inputs resident in HBM
     sampler = ClockSampler(local_rank)
     sampler.start()
-    n_gemm_slots = 64 * CFG2["n_layer"] * K + 64
+    n_gemm_slots = 64 * CFG["n_layer"] * K + 64
     lib.me_profile_enable(n_gemm_slots)
     launches0 = _lib.launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -316,23 +355,22 @@ def main():
 
     if rank == 0:
         peaks = load_peaks()
-        tokens_per_step = world * B * L
+        tokens_per_step = world * B * Ls     # positions through the stack (continuous_token: two of them are the condition)
         value = tokens_per_step * K / (ms / 1e3)
         e2e = tokens_per_step * K / (ms_e2e / 1e3)
         h2d = sum(t.numel() * t.element_size() for t in host[0])
-        fpt = 3 * flops_per_token(CFG2, L)
+        fpt = 3 * flops_per_token(CFG, Ls)
         gemm_tflops = (g_fl.value / 1e12) / (g_ms.value / 1e3) if g_ms.value > 0 else 0.0
         traffic = None
         tpath = os.path.join(ROOT, "profiles", "gemm_traffic.json")
         if os.path.exists(tpath):   # dram__bytes_read+write per launch from the committed ncu --set full capture
             traffic = json.load(open(tpath))["mean_dram_bytes_per_launch"]
         line = {
-            "metric": METRIC, "value": value, "unit": "tokens/s", "n_gpus": world, "steps": K, "warmup": W,
+            "metric": metric, "value": value, "unit": "tokens/s", "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "bf16", "data": "synthetic",
-            "config": {"workload": "train step (fwd+CE+bwd+allreduce+clip+Adam) continuous_concat 12L/768d/12h "
-                                   "seq1024 batch32/GPU bf16 (BASELINE configs[1])",
-                       "global_batch": world * B, "seq_len": L, "parallelism": f"dp{world}",
+            "config": {"workload": "train step (fwd+CE+bwd+allreduce+clip+Adam) " + label,
+                       "global_batch": world * B, "seq_len": Ls, "parallelism": f"dp{world}",
                        "l2": "per-step working set (activations > 10 GB) far exceeds the 126 MB L2; no flush needed",
                        "attention": args.attn, "loss": "torch" if args.torch_loss else "fused", "final_loss": final_loss},
             "e2e": {"value": e2e, "unit": "tokens/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
@@ -346,12 +384,12 @@ def main():
                          "whole_step_tflops": value * fpt / 1e12,
                          "whole_step_frac": value * fpt / 1e12 / peaks["tf_sustained"] / world},
         }
-        if world == 1 and not args.no_decode:
+        if world == 1 and not args.no_decode and args.workload == "cfg2":
             line["decode"] = decode_leg(model, peaks)
         if world == 1 and not args.no_cpu_baseline:
-            tps, cms, threads = cpu_train_tokens_per_s(steps=2, warmup=1, B=1)
+            tps, cms, threads = cpu_train_tokens_per_s(steps=2, warmup=1, B=1, L=L, cfg=CFG)
             line["cpu_baseline"] = {"value": tps, "unit": "tokens/s", "cores": threads, "kind": "port",
-                                    "sample": f"2 steps of batch 1 x seq {L}, same model, fp32, {threads} threads",
+                                    "sample": f"2 steps of batch 1 x seq {Ls}, same model, fp32, {threads} threads",
                                     "ms_per_step": cms}
         print(json.dumps(line), flush=True)
     if world > 1:

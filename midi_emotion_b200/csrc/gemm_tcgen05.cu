@@ -325,6 +325,14 @@ int launch_gemm_bf16(const void* A, const void* B, void* D, int M, int N, int K,
   ME_CHECK(lda % 8 == 0 && ldb % 8 == 0, "me_gemm_bf16: operand row pitches must be multiples of 8 elements (lda=%d ldb=%d)", lda, ldb);
   ME_CHECK((reinterpret_cast<uintptr_t>(A) & 15) == 0 && (reinterpret_cast<uintptr_t>(B) & 15) == 0,
            "me_gemm_bf16: operands must be 16-byte aligned");
+  // the epilogues use 16-byte stores / loads / reductions whenever the row pitch allows them
+  const int d_vec = out_dtype == ME_BF16 ? 8 : 4;
+  ME_CHECK(ldd % d_vec != 0 || (reinterpret_cast<uintptr_t>(D) & 15) == 0,
+           "me_gemm_bf16: output must be 16-byte aligned (row pitch %d allows vector stores)", ldd);
+  ME_CHECK(!(flags & ME_EPI_ADD_F32) || ldd % 4 != 0 || (reinterpret_cast<uintptr_t>(addend) & 15) == 0,
+           "me_gemm_bf16: addend must be 16-byte aligned");
+  ME_CHECK(!(flags & ME_EPI_RELU_MASK) || ldmask % 8 != 0 || (reinterpret_cast<uintptr_t>(relu_mask) & 15) == 0,
+           "me_gemm_bf16: ReLU mask must be 16-byte aligned");
   ME_CHECK(!(flags & ME_EPI_BIAS) || bias, "me_gemm_bf16: bias flag without pointer");
   ME_CHECK(!(flags & ME_EPI_ADD_F32) || addend, "me_gemm_bf16: addend flag without pointer");
   ME_CHECK(!(flags & ME_EPI_RELU_MASK) || relu_mask, "me_gemm_bf16: mask flag without pointer");

@@ -1,0 +1,97 @@
+"""bench.py's host-side contract, checked without a GPU: the workload table against BASELINE.json / SURVEY.md 8(d),
+the synthetic batch contract of each conditioning mode (loader.py:55-75,169-195 as restated in SURVEY.md A0) and the
+JSON line of the reference arm."""
+import json
+import math
+import os
+import subprocess
+import sys
+
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import bench  # noqa: E402
+
+
+def test_algorithmic_flops_match_the_survey_figures():
+    # cfg2 199.7 MFLOP/token forward, 599.2 fwd+bwd, 19.63 TFLOP per 32 x 1024 step; cfg3 757.0 / 2271.1
+    f2 = bench.flops_per_token(bench.CFG2, 1024)
+    assert abs(f2 / 1e6 - 199.7) < 0.05
+    assert abs(3 * f2 / 1e6 - 599.2) < 0.1
+    assert abs(3 * f2 * 32 * 1024 / 1e12 - 19.63) < 0.01
+    f3 = bench.flops_per_token(bench.CFG3, 2048)
+    assert abs(f3 / 1e6 - 757.0) < 0.05 and abs(3 * f3 / 1e6 - 2271.1) < 0.1
+
+
+def test_default_workload_is_baseline_configs_1():
+    cfg, L, Ls, B, metric, label = bench.workload("cfg2")
+    assert (cfg["n_layer"], cfg["d_model"], cfg["n_head"], cfg["d_inner"]) == (12, 768, 12, 3072)
+    assert cfg["conditioning"] == "continuous_concat" and cfg["d_condition"] == 192 and cfg["vocab_size"] == 1007
+    assert (L, Ls, B) == (1024, 1024, 32)
+    base = json.load(open(os.path.join(ROOT, "BASELINE.json")))
+    assert metric in base["metric"] and "configs[1]" in label
+
+
+def test_cfg3_and_sweep_workloads():
+    cfg, L, Ls, B, metric, _ = bench.workload("cfg3")
+    assert (cfg["n_layer"], cfg["d_model"], cfg["n_head"], L, Ls) == (24, 1024, 16, 2048, 2048)
+    assert "seq2048" in metric
+    for mode in ("discrete_token", "continuous_token", "none"):
+        cfg, L, Ls, B, metric, label = bench.workload(mode)
+        assert cfg["conditioning"] == mode and cfg["d_condition"] == -1 and Ls == 1024 and "configs[4]" in label
+        assert cfg["vocab_size"] == (1017 if mode == "discrete_token" else 1007)
+        assert L == (1022 if mode == "continuous_token" else 1024)
+
+
+@pytest.mark.parametrize("mode", ["continuous_concat", "discrete_token", "continuous_token", "none"])
+def test_synthetic_batch_contract(mode):
+    name = "cfg2" if mode == "continuous_concat" else mode
+    cfg, L, Ls, _, _, _ = bench.workload(name)
+    tokens, cond, target = bench.synthetic_batch(cfg, 3, L, seed=5)
+    assert tokens.shape == (3, L) and tokens.dtype == torch.int64 and cond.shape == (3, 2)
+    assert target.shape == (3, Ls) and target.dtype == torch.int64
+    assert int(tokens.min()) >= 1 and int(tokens.max()) < cfg["vocab_size"]
+    shift = Ls - L
+    assert torch.equal(target[:, shift:-1], tokens[:, 1:])            # next-token targets
+    if mode == "continuous_token":
+        assert int(target[:, :2].abs().sum()) == 0                     # the two condition positions predict nothing
+    if mode == "discrete_token":
+        assert bool(((tokens[:, 0] >= 1007) & (tokens[:, 0] <= 1016)).all())
+        assert int(tokens[:, 1:].max()) < 1007
+    else:
+        assert bool((tokens[:, 0] == 1).all())                          # <START>
+    if mode in ("none", "discrete_token"):
+        assert bool(torch.isnan(cond).all())
+    else:
+        assert bool(((cond >= -1) & (cond <= 1)).all())
+    again = bench.synthetic_batch(cfg, 3, L, seed=5)
+    assert torch.equal(again[0], tokens) and torch.equal(again[2], target)
+
+
+def test_reference_arm_prints_one_contract_line(monkeypatch, capsys):
+    """`bench.py --impl reference` (oracle port on the host cores) on a shrunk model: one JSON line with the keys the
+    driver reads."""
+    small = dict(bench.CFG2, n_layer=1, d_model=64, n_head=2, d_inner=128, d_condition=16)
+    monkeypatch.setattr(bench, "workload", lambda name: (small, 48, 48, 2, bench.METRIC, "shrunk"))
+
+    class A:
+        steps, warmup, gpus, workload = 1, 0, 1, "cfg2"
+    bench.run_reference(A, rank=1)
+    assert capsys.readouterr().out == ""                                # other ranks print nothing
+    bench.run_reference(A, rank=0)
+    lines = [ln for ln in capsys.readouterr().out.splitlines() if ln.strip()]
+    assert len(lines) == 1
+    j = json.loads(lines[0])
+    assert j["impl"] == "reference" and j["unit"] == "tokens/s" and j["higher_is_better"] is True
+    assert j["value"] > 0 and math.isfinite(j["value"]) and j["gpu_launches"] == 0
+    assert j["cpu_baseline"]["kind"] == "port" and j["cpu_baseline"]["cores"] >= 1
+    assert j["e2e"] == {"value": j["value"], "unit": "tokens/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+
+
+def test_b200_arm_refuses_to_run_without_a_gpu():
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--steps", "1"], capture_output=True, text=True)
+    assert r.returncode != 0 and "no CUDA device" in (r.stderr + r.stdout)

@@ -123,6 +123,24 @@ def test_gemm_rejects_misaligned_operands():
         gemm_bf16(A, B, 64, 64, 70, 0, 0, ME_F32)
 
 
+def test_gemm_output_alignment_is_an_error_not_a_fault():
+    """A row pitch that allows 16-byte stores with a base pointer that does not is refused up front; an odd
+    pitch (scalar stores) works from any 4-byte aligned base."""
+    M, N, K = 128, 64, 64
+    A, B, As, Bs = _operands(M, N, K, 0, 0, seed=11)
+    want = A.float() @ B.float().t()
+    buf = torch.zeros(M * 68 + 8, device="cuda")
+    off = buf[1:]                                               # 4-byte offset from a 16-byte aligned allocation
+    with pytest.raises(RuntimeError, match="16-byte aligned"):
+        _lib.call("me_gemm_bf16_ex", ptr(As), ptr(Bs), ptr(off), M, N, K, K, K, 68, 0, 0, ME_F32, 0, None, None, None, 0,
+                  0, 0, stream())
+    _lib.call("me_gemm_bf16_ex", ptr(As), ptr(Bs), ptr(off), M, N, K, K, K, 67, 0, 0, ME_F32, 0, None, None, None, 0,
+              0, 0, stream())
+    torch.cuda.synchronize()
+    got = off[:M * 67].view(M, 67)[:, :N]
+    assert rel_err(got, want) < 1e-5
+
+
 @pytest.mark.parametrize("a_mn,b_mn", [(0, 0), (0, 1), (1, 1), (1, 0)])
 def test_gemm_f32_simt(a_mn, b_mn):
     M, N, K = 150, 203, 77
