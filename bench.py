@@ -29,6 +29,7 @@ CFG2 = dict(vocab_size=1007, n_layer=12, n_head=12, d_model=768, d_inner=3072, d
 SEQ_LEN = 1024
 BATCH_PER_GPU = 32
 METRIC = "MIDI tokens/sec train fwd+bwd @ seq1024"
+DEFAULT_OPTIM = "torch"
 CFG3 = dict(vocab_size=1007, n_layer=24, n_head=16, d_model=1024, d_inner=4096, dropout=0.1, d_condition=192,
             conditioning="continuous_concat")
 
@@ -253,6 +254,8 @@ def main():
     ap.add_argument("--attn", default="auto", choices=["auto", "simt", "tensor"])
     ap.add_argument("--no-decode", action="store_true", help="skip the KV-cache decode measurement (configs[3])")
     ap.add_argument("--torch-loss", action="store_true", help="PyTorch cross-entropy instead of the fused kernel")
+    ap.add_argument("--optim", default=DEFAULT_OPTIM, choices=["torch", "fused"],
+                    help="torch: clip_grad_norm_ + torch.optim.Adam(fused=True); fused: ClipAdam (csrc/optimizer.cu)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -264,7 +267,7 @@ def main():
         raise SystemExit("bench.py: no CUDA device (the B200 path has no CPU fallback)")
 
     import torch.distributed as dist
-    from midi_emotion_b200 import _lib, build_model, cross_entropy
+    from midi_emotion_b200 import ClipAdam, _lib, build_model, cross_entropy
     from midi_emotion_b200.ddp import DataParallel
 
     torch.cuda.set_device(local_rank)
@@ -288,7 +291,11 @@ def main():
     model = model.to(dev).train()
     model.attn_impl = args.attn
     ddp = DataParallel(model)
-    opt = torch.optim.Adam(model.parameters(), lr=2e-5, fused=True)
+    # train.py:182 Adam (lr 2e-5, config.py:43) and the clip at 1.0 of train.py:321-322
+    if args.optim == "fused":
+        opt = ClipAdam(model.parameters(), lr=2e-5, max_grad_norm=1.0)
+    else:
+        opt = torch.optim.Adam(model.parameters(), lr=2e-5, fused=True)
 
     host = [synthetic_batch(CFG, B, L, 1002 + 17 * rank + i, pin=True) for i in range(2)]
     resident = [tuple(t.to(dev) for t in h) for h in host]
@@ -303,7 +310,8 @@ def main():
             loss = cross_entropy(logits, target, ignore_index=0)
         loss.backward()
         ddp.sync_gradients()
-        torch.nn.utils.clip_grad_norm_(model.parameters(), 1.0)
+        if args.optim == "torch":
+            torch.nn.utils.clip_grad_norm_(model.parameters(), 1.0)
         opt.step()
         opt.zero_grad(set_to_none=True)
         return loss
@@ -372,7 +380,8 @@ def main():
             "config": {"workload": "train step (fwd+CE+bwd+allreduce+clip+Adam) " + label,
                        "global_batch": world * B, "seq_len": Ls, "parallelism": f"dp{world}",
                        "l2": "per-step working set (activations > 10 GB) far exceeds the 126 MB L2; no flush needed",
-                       "attention": args.attn, "loss": "torch" if args.torch_loss else "fused", "final_loss": final_loss},
+                       "attention": args.attn, "loss": "torch" if args.torch_loss else "fused", "optimizer": args.optim,
+                       "final_loss": final_loss},
             "e2e": {"value": e2e, "unit": "tokens/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
                     "ms_per_step": ms_e2e / K},
             "gpu_launches": int(launches),
@@ -387,9 +396,9 @@ def main():
         if world == 1 and not args.no_decode and args.workload == "cfg2":
             line["decode"] = decode_leg(model, peaks)
         if world == 1 and not args.no_cpu_baseline:
-            tps, cms, threads = cpu_train_tokens_per_s(steps=2, warmup=1, B=1, L=L, cfg=CFG)
+            tps, cms, threads = cpu_train_tokens_per_s(steps=6, warmup=1, B=1, L=L, cfg=CFG)
             line["cpu_baseline"] = {"value": tps, "unit": "tokens/s", "cores": threads, "kind": "port",
-                                    "sample": f"2 steps of batch 1 x seq {Ls}, same model, fp32, {threads} threads",
+                                    "sample": f"6 steps of batch 1 x seq {Ls}, same model, fp32, {threads} threads",
                                     "ms_per_step": cms}
         print(json.dumps(line), flush=True)
     if world > 1:

@@ -327,6 +327,46 @@ int me_sizeof_sample_args(void);
 int me_cross_entropy(const void* logits, int dtype, int M, int V, int ld, const int64_t* targets,
                      int64_t ignore_index, void* grad_logits, int ld_grad, float* stats, void* stream);
 
+/* ---------------------------------------------------------------------------------------
+ * Optimiser step of the training loop, train.py:319-325:
+ *     scaler.unscale_(optimizer); clip_grad_norm_(model.parameters(), clip); scaler.step(optimizer)
+ * with optimizer = torch.optim.Adam (train.py:182), over ALL parameter tensors in a handful of launches
+ * (the reference's sequence is ~10 foreach launches per 50-tensor chunk plus two host synchronisations
+ * inside GradScaler).  Three calls:
+ *   1. me_grad_sqnorm_partials: one fp32 partial sum of (grad / grad_scale)^2 per 8192-element chunk;
+ *   2. me_adam_prepare (one thread block): total_norm = sqrt(sum of the partials), the clip coefficient
+ *      min(1, max_grad_norm / (total_norm + 1e-6)) (torch.nn.utils.clip_grad_norm_), the skip decision
+ *      (non-finite norm: GradScaler.step would skip the update, train.py:323) and, when not skipped,
+ *      step += 1 and the bias-correction scalars of that step -- no host round trip anywhere;
+ *   3. me_adam_update: g = grad / grad_scale * coef (+ weight_decay * p);
+ *      m = m + (1 - beta1)(g - m); v = beta2 v + (1 - beta2) g^2;
+ *      p -= (lr / (1 - beta1^step)) * m / (sqrt(v) / sqrt(1 - beta2^step) + eps)      (torch.optim.Adam)
+ *      Gradients are read-only (the clipped values are not written back; the reference zeroes them next,
+ *      train.py:325).
+ * `tensors` is a HOST array (pointers travel in kernel-parameter space, 64 tensors per launch); all
+ * tensor pointers are DEVICE fp32, contiguous.  stats: DEVICE f32[8], written by me_adam_prepare:
+ *   [0] total_norm  [1] clip coefficient  [2] 1 if the step is skipped else 0  [3] step count after this call
+ *   [4] lr / (1 - beta1^step)  [5] sqrt(1 - beta2^step)  [6..7] reserved
+ * step_dev: DEVICE f32[1], the number of updates applied so far (torch keeps `step` as a float32 tensor too).
+ * ------------------------------------------------------------------------------------- */
+typedef struct me_adam_tensor {
+  float* param;
+  const float* grad;
+  float* exp_avg;
+  float* exp_avg_sq;
+  int64_t numel;
+} me_adam_tensor;
+/* number of partial sums me_grad_sqnorm_partials writes for this tensor list (negative on bad input) */
+int64_t me_grad_sqnorm_chunks(const me_adam_tensor* tensors, int n);
+int me_grad_sqnorm_partials(const me_adam_tensor* tensors, int n, double grad_scale, float* partials,
+                            int64_t partials_capacity, void* stream);
+/* n_partials == 0 (partials may be NULL): no norm was taken, total_norm is reported as 0 and nothing is clipped;
+ * max_grad_norm <= 0: no clipping (the non-finite check still applies when partials are given). */
+int me_adam_prepare(const float* partials, int64_t n_partials, double max_grad_norm, double lr, double beta1,
+                    double beta2, float* step_dev, float* stats, void* stream);
+int me_adam_update(const me_adam_tensor* tensors, int n, double beta1, double beta2, double eps,
+                   double weight_decay, double grad_scale, const float* stats, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

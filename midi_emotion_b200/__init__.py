@@ -10,6 +10,7 @@ from .transformer import MusicTransformer, positional_table, set_dropout  # noqa
 from .decode import KVCacheDecoder  # noqa: F401
 from .sampling import Sampler, generate  # noqa: F401
 from .loss import cross_entropy  # noqa: F401
+from .optim import ClipAdam  # noqa: F401
 
-__all__ = ["build_model", "MusicTransformer", "KVCacheDecoder", "Sampler", "generate", "cross_entropy", "set_dropout",
+__all__ = ["build_model", "MusicTransformer", "KVCacheDecoder", "Sampler", "generate", "cross_entropy", "ClipAdam", "set_dropout",
            "positional_table", "CONDITIONINGS"]

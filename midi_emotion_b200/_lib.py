@@ -56,6 +56,10 @@ class SampleArgs(C.Structure):
                 ("out_probs", _vp), ("stream", _vp)]
 
 
+class AdamTensor(C.Structure):
+    _fields_ = [("param", _vp), ("grad", _vp), ("exp_avg", _vp), ("exp_avg_sq", _vp), ("numel", _i64)]
+
+
 class LayerArgs(C.Structure):
     _fields_ = [
         ("dtype", _i32), ("attn_impl", _i32), ("training", _i32), ("_pad0", _i32),
@@ -117,6 +121,11 @@ _PROTOS = {
     "me_cross_entropy_forward_backward": (C.c_int, [_vp, C.c_int, C.c_int, C.c_int, C.c_int, _vp, C.c_int, _f32,
                                                     _vp, _vp, _vp, _vp]),
     "me_sample_step": (C.c_int, None),
+    "me_grad_sqnorm_chunks": (C.c_int64, [C.POINTER(AdamTensor), C.c_int]),
+    "me_grad_sqnorm_partials": (C.c_int, [C.POINTER(AdamTensor), C.c_int, C.c_double, _vp, C.c_int64, _vp]),
+    "me_adam_prepare": (C.c_int, [_vp, C.c_int64, C.c_double, C.c_double, C.c_double, C.c_double, _vp, _vp, _vp]),
+    "me_adam_update": (C.c_int, [C.POINTER(AdamTensor), C.c_int, C.c_double, C.c_double, C.c_double, C.c_double,
+                                 C.c_double, _vp, _vp]),
 }
 
 # symbols every build must export (checked by the CPU test-suite against include/*.h)
