@@ -29,7 +29,7 @@ CFG2 = dict(vocab_size=1007, n_layer=12, n_head=12, d_model=768, d_inner=3072, d
 SEQ_LEN = 1024
 BATCH_PER_GPU = 32
 METRIC = "MIDI tokens/sec train fwd+bwd @ seq1024"
-DEFAULT_OPTIM = "torch"
+DEFAULT_OPTIM = "fused"
 CFG3 = dict(vocab_size=1007, n_layer=24, n_head=16, d_model=1024, d_inner=4096, dropout=0.1, d_condition=192,
             conditioning="continuous_concat")
 

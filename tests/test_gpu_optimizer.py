@@ -141,7 +141,7 @@ def test_state_dict_moves_between_clip_adam_and_torch_adam():
     ref = torch.optim.Adam(theirs, lr=1e-3)
     ref.load_state_dict(sd)
     again = ClipAdam([torch.nn.Parameter(p.detach().clone()) for p in ours], lr=1e-3)
-    again.load_state_dict(ref.state_dict())
+    again.load_state_dict(copy.deepcopy(ref.state_dict()))     # (load_state_dict aliases the tensors it is given)
     mine = again.param_groups[0]["params"]
     for params in (ours, theirs, mine):
         _set_grads(params, 400, 0.1)
