@@ -265,7 +265,7 @@ add_ln_fwd_kernel(const float* __restrict__ x_res, const T* __restrict__ y, cons
 // keeps occupancy high enough to cover HBM latency); the strips are summed per block at the end and
 // flushed with one atomicAdd per column per block.
 template <typename T, int NCH>
-__global__ void __launch_bounds__(LN_THREADS)
+__global__ void __launch_bounds__(LN_THREADS, 2)   // two blocks per SM (<= 128 registers): the kernel lives on occupancy
 add_ln_bwd_kernel(const float* __restrict__ dout, const float* __restrict__ dout_add,
                   const bf16* __restrict__ dout_add_T, const float* __restrict__ z,
                   const float* __restrict__ mean, const float* __restrict__ rstd, const float* __restrict__ gamma,
