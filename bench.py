@@ -186,6 +186,29 @@ def run_reference(args, rank):
     print(json.dumps(line), flush=True)
 
 
+def cpu_decode_tokens_per_s(prefix=1024, B=4, steps=2, threads=None):
+    """The reference's decode step on the host cores: generate.py:99-122 re-runs the model on the whole prefix for
+    every generated token (no KV cache), so one step at prefix length t costs a full forward pass over [B, t].
+    Timed at the same mid-sequence prefix as the GPU decode leg, on a reduced batch."""
+    from oracle import midi_oracle as O
+    threads = threads or os.cpu_count() or 1
+    torch.set_num_threads(threads)
+    cfg = dict(CFG2, dropout=0.0)
+    params = O.init_params(cfg, seed=1234, e_scale=0.2)
+    g = torch.Generator().manual_seed(1004)
+    tok = torch.randint(1, cfg["vocab_size"], (B, prefix), generator=g)
+    tok[:, 0] = 1
+    cond = torch.rand(B, 2, generator=g) * 2 - 1
+    O.decode_last_logits(params, cfg, tok[:, :64], cond)          # warm-up (thread pool, allocator)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        O.decode_last_logits(params, cfg, tok, cond)
+    dt = (time.perf_counter() - t0) / steps
+    return {"value": B / dt, "unit": "tokens/s", "cores": threads, "kind": "port", "ms_per_step": 1e3 * dt,
+            "sample": f"{steps} steps of the no-cache full-prefix recompute (generate.py:99-122) at prefix {prefix}, "
+                      f"batch {B}, same model, fp32, {threads} threads"}
+
+
 # ----------------------------------------------------------------------------------------------
 # decode leg (BASELINE configs[3]): KV-cache step at B=256, T=2048, measured mid-sequence
 # ----------------------------------------------------------------------------------------------
@@ -395,6 +418,11 @@ def main():
         }
         if world == 1 and not args.no_decode and args.workload == "cfg2":
             line["decode"] = decode_leg(model, peaks)
+            if not args.no_cpu_baseline:
+                try:
+                    line["decode"]["cpu_baseline"] = cpu_decode_tokens_per_s()
+                except Exception as e:   # a reported baseline must never cost the measured line
+                    line["decode"]["cpu_baseline"] = {"error": repr(e)}
         if world == 1 and not args.no_cpu_baseline:
             tps, cms, threads = cpu_train_tokens_per_s(steps=6, warmup=1, B=1, L=L, cfg=CFG)
             line["cpu_baseline"] = {"value": tps, "unit": "tokens/s", "cores": threads, "kind": "port",

@@ -95,3 +95,16 @@ def test_b200_arm_refuses_to_run_without_a_gpu():
         pytest.skip("a GPU is present")
     r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--steps", "1"], capture_output=True, text=True)
     assert r.returncode != 0 and "no CUDA device" in (r.stderr + r.stdout)
+
+
+def test_decode_cpu_baseline_is_the_no_cache_recompute(monkeypatch):
+    small = dict(bench.CFG2, n_layer=1, d_model=64, n_head=2, d_inner=128, d_condition=16)
+    monkeypatch.setattr(bench, "CFG2", small)
+    n = torch.get_num_threads()
+    try:
+        r = bench.cpu_decode_tokens_per_s(prefix=80, B=2, steps=1, threads=2)
+    finally:
+        torch.set_num_threads(n)
+    assert r["kind"] == "port" and r["cores"] == 2 and r["unit"] == "tokens/s"
+    assert r["value"] > 0 and math.isfinite(r["value"]) and "prefix 80" in r["sample"]
+    assert r["value"] == pytest.approx(2 / (r["ms_per_step"] / 1e3))
