@@ -90,3 +90,24 @@ def test_product_does_not_import_the_oracle():
             if f.endswith((".py", ".cu", ".cuh")):
                 src = open(os.path.join(dirpath, f)).read()
                 assert "oracle" not in src.replace("no oracle", ""), f
+
+
+def test_build_digest_does_not_depend_on_where_the_tree_lives(tmp_path):
+    """The GPU box runs from a copy of the tree at another path: the library built here must be recognised as current
+    there (otherwise every process -- every rank of a torchrun launch -- would rebuild it concurrently)."""
+    import shutil
+    import subprocess
+    import sys
+    from midi_emotion_b200 import build as b
+    b.build()
+    here = b._digest()
+    assert open(os.path.join(b.LIBDIR, "build.sha256")).read().strip() == here
+    pkg = tmp_path / "midi_emotion_b200"
+    pkg.mkdir()
+    shutil.copy(os.path.join(ROOT, "midi_emotion_b200", "build.py"), pkg / "build.py")
+    (pkg / "__init__.py").write_text("")
+    shutil.copytree(os.path.join(ROOT, "midi_emotion_b200", "csrc"), pkg / "csrc")
+    shutil.copytree(os.path.join(ROOT, "include"), tmp_path / "include")
+    out = subprocess.run([sys.executable, "-c", "from midi_emotion_b200 import build as b; print(b._digest())"],
+                         cwd=tmp_path, capture_output=True, text=True, check=True).stdout.strip()
+    assert out == here
