@@ -79,7 +79,8 @@ class ClipAdam(torch.optim.Optimizer):
     @torch.no_grad()
     def step(self, closure=None, grad_scale: float = 1.0):
         """Applies one update; returns the total gradient norm (0-d device tensor, the value clip_grad_norm_
-        returns; zero when neither clipping nor a gradient scale asked for it).  `grad_scale`: the gradients are
+        returns; zero when neither clipping nor a gradient scale asked for it; a view of `last_stats`, valid until
+        the next step -- clone it to keep it).  `grad_scale`: the gradients are
         divided by it first (GradScaler.unscale_).  When a norm is taken, a non-finite norm skips the update and
         leaves the step count unchanged, as GradScaler.step does."""
         loss = None
