@@ -11,3 +11,4 @@ run model_bf16 tests/test_gpu_model.py -k "bf16"
 run decode tests/test_gpu_decode.py
 run fullsize tests/test_gpu_fullsize.py
 run sampling_loss tests/test_gpu_sampling.py tests/test_gpu_loss.py
+run optimizer tests/test_gpu_optimizer.py

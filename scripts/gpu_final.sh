@@ -1,6 +1,5 @@
 #!/bin/bash
-# Round-end validation in one gpurun call: new optimiser tests first, then the whole GPU suite in one process (the way
-# the driver runs it), the bench line with either optimiser, the extra workloads (configs[2], configs[4] sweep), and an
+# Round-end validation in one gpurun call: the whole GPU suite in one process (the way the driver runs it), the bench line with either optimiser, the extra workloads (configs[2], configs[4] sweep), and an
 # ncu capture of the optimiser kernels.  Every piece runs under its own timeout.
 mkdir -p gpurun_out
 T0=$SECONDS
