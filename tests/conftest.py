@@ -16,7 +16,7 @@ def pytest_configure(config):
 
 def golden_names():
     return sorted(f[:-4] for f in os.listdir(GOLDEN_DIR)
-                  if f.endswith(".npz") and not f.startswith(("pe_", "sampling_", "ce_")))
+                  if f.endswith(".npz") and not f.startswith(("pe_", "sampling_", "ce_", "regression_")))
 
 
 def sampling_golden_names():
@@ -80,3 +80,23 @@ def ce_golden(request):
 @pytest.fixture(params=sampling_golden_names())
 def sampling_golden(request):
     return load_sampling_golden(request.param)
+
+
+def regression_golden_names():
+    return sorted(f[:-4] for f in os.listdir(GOLDEN_DIR) if f.startswith("regression_") and f.endswith(".npz"))
+
+
+@pytest.fixture(params=regression_golden_names())
+def regression_golden(request):
+    import numpy as np
+    import torch
+
+    z = np.load(os.path.join(GOLDEN_DIR, request.param + ".npz"))
+    cfg = {}
+    for k, v in zip(z["cfg_keys"], z["cfg_vals"]):
+        k, v = str(k), str(v)
+        cfg[k] = v if k == "conditioning" else (v == "True") if k == "regression" else float(v) if k == "dropout" else int(v)
+    return dict(cfg=cfg, tokens=torch.from_numpy(z["tokens"]), out_fp32=torch.from_numpy(z["out_fp32"]),
+                out_bf16=torch.from_numpy(z["out_bf16"]), loss_fp32=float(z["loss_fp32"]),
+                params={k[len("param::"):]: torch.from_numpy(z[k]) for k in z.files if k.startswith("param::")},
+                grads={k[len("grad::"):]: torch.from_numpy(z[k]) for k in z.files if k.startswith("grad::")})

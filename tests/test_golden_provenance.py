@@ -43,3 +43,11 @@ def test_reference_reproduces_the_golden_vectors(golden, ref_build_model):
     top = max(float(v.abs().max()) for v in g["grads"].values())
     for n, p in model.named_parameters():
         torch.testing.assert_close(p.grad, g["grads"][n], rtol=1e-4, atol=1e-6 * max(1.0, top), msg=lambda m: f"{n}: {m}")
+
+
+def test_reference_reproduces_the_regression_goldens(regression_golden, ref_build_model):
+    g = regression_golden
+    model, _ = ref_build_model(dict(g["cfg"]))
+    model.load_state_dict(g["params"], strict=True)
+    model.eval()
+    torch.testing.assert_close(model(g["tokens"]).detach(), g["out_fp32"], rtol=1e-5, atol=1e-6)

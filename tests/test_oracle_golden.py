@@ -103,3 +103,29 @@ def test_train_step_changes_params_and_is_finite(golden):
     assert np.isfinite(float(loss))
     moved = sum(float((newp[k] - g["params"][k]).abs().max()) > 0 for k in newp)
     assert moved > len(newp) // 2
+
+
+# ---- regression side model (models/music_regression.py): oracle only, no CUDA path yet
+def test_regression_oracle_matches_reference(regression_golden):
+    g = regression_golden
+    assert {k: tuple(v.shape) for k, v in g["params"].items()} == O.regression_param_shapes(g["cfg"])
+    out = O.regression_forward(g["params"], g["cfg"], g["tokens"])
+    torch.testing.assert_close(out, g["out_fp32"], rtol=1e-5, atol=1e-6)
+    out16 = O.regression_forward(g["params"], g["cfg"], g["tokens"], autocast=torch.bfloat16)
+    torch.testing.assert_close(out16.float(), g["out_bf16"], rtol=2e-2, atol=2e-2)
+
+
+def test_regression_oracle_gradients_and_unmasked_pads(regression_golden):
+    g = regression_golden
+    leaves = {k: v.clone().requires_grad_(True) for k, v in g["params"].items()}
+    out = O.regression_forward(leaves, g["cfg"], g["tokens"])
+    loss = ((out - torch.tensor([[0.8, -0.8]])) ** 2).mean()
+    assert float(loss.detach()) == pytest.approx(g["loss_fp32"], rel=1e-5)
+    loss.backward()
+    top = max(float(v.abs().max()) for v in g["grads"].values())
+    for k, v in leaves.items():
+        torch.testing.assert_close(v.grad, g["grads"][k], rtol=1e-4, atol=1e-6 * max(1.0, top), msg=lambda m: f"{k}: {m}")
+    # no mask at all (music_regression.py:78): changing a pad position at the tail changes the pooled first position
+    tok2 = g["tokens"].clone()
+    tok2[0, -1] = 5
+    assert not torch.equal(O.regression_forward(g["params"], g["cfg"], tok2)[0], out.detach()[0])
