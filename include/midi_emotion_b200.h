@@ -35,6 +35,14 @@ extern "C" {
 #define ME_ATTN_SIMT 0    /* exact-order fp32 SIMT kernels (fp32 parity path, any dtype) */
 #define ME_ATTN_TENSOR 1  /* bf16 tensor-core kernels */
 
+/* attention flags (me_attn_args.flags, me_layer_args.attn_flags) */
+#define ME_ATTN_NONCAUSAL 1     /* every key is visible to every query (models/music_regression.py:78, no_mask=True:
+                                 * mask = None); the relative term keeps its lower-triangular support, Srel[i,j] = 0
+                                 * for j > i (_qe_masking, music_regression.py:256-262)                              */
+#define ME_ATTN_REF_ROUNDING 2  /* ME_ATTN_TENSOR forward only: round QK^T, Srel, their sum and the scaled logits to
+                                 * bf16 exactly where the reference does under autocast (music_multi.py:215-222);
+                                 * default keeps them in fp32 (more accurate, fewer instructions)                    */
+
 /* GEMM epilogue flags */
 #define ME_EPI_BIAS 1        /* += bias[n] (fp32)                          */
 #define ME_EPI_RELU 2        /* max(.,0)                                   */
@@ -144,6 +152,7 @@ int me_convert_batched(const me_convert_desc* table_dev, int n, void* stream);
  * Relative global attention (Music Transformer), causal + key-pad mask, fused:
  *   S[i,j] = (q_i.k_j + q_i.E[max_seq-1-(i-j)]) / sqrt(dh),  j <= i and !keypad[b,j]
  *   O = softmax(S) V
+ * With ME_ATTN_NONCAUSAL every key j < Lk is visible (regression side model) and the E term is 0 for j > i.
  * Replaces music_multi.py:211-235 (_get_left_embedding, einsum, _qe_masking, _skewing, QK^T,
  * mask add, softmax, .V, head merge).  q/k/v are addressed with element strides so that they
  * may live in a packed QKV buffer [B, Lq, 3, H, dh] or in a KV cache [B, H, T, dh].
@@ -153,7 +162,7 @@ int me_convert_batched(const me_convert_desc* table_dev, int n, void* stream);
  * ------------------------------------------------------------------------------------- */
 typedef struct me_attn_args {
   int32_t dtype, impl;
-  int32_t B, H, Lq, Lk, dh, max_seq, q_pos0, _pad;
+  int32_t B, H, Lq, Lk, dh, max_seq, q_pos0, flags; /* flags: ME_ATTN_* bits */
   const void *q, *k, *v, *E;
   int64_t q_sb, q_sh, q_si; /* element strides: batch, head, row */
   int64_t k_sb, k_sh, k_sj;
@@ -195,7 +204,7 @@ int me_debug_trace_set(long long* device_buf);
  * biases / LN affine fp32.  Saved tensors are consumed by me_layer_backward.
  * ------------------------------------------------------------------------------------- */
 typedef struct me_layer_args {
-  int32_t dtype, attn_impl, training, _pad0;
+  int32_t dtype, attn_impl, training, attn_flags; /* attn_flags: ME_ATTN_* bits */
   int32_t B, Ls, d, H, d_inner, max_seq;
   float dropout_p, ln_eps;
   uint64_t seed;
@@ -326,6 +335,55 @@ int me_sizeof_sample_args(void);
  * ------------------------------------------------------------------------------------- */
 int me_cross_entropy(const void* logits, int dtype, int M, int V, int ld, const int64_t* targets,
                      int64_t ignore_index, void* grad_logits, int ld_grad, float* stats, void* stream);
+
+/* ---------------------------------------------------------------------------------------
+ * Token pipeline of the training loader, data/loader.py:132-195 (Loader.__getitem__ after its random draws) with
+ * data/data_processing.py:225-247 (transpose, tensor_to_ind_tensor), for a whole batch in one launch: transpose
+ * the pitches of transposable events, map every (event, value) tuple to its token id, prepend the caller-built
+ * prefix (<START> when the sample starts at a bar, <CLS>, the two emotion tokens of discrete_token), crop /
+ * trim to input_len + 1, pad, and split into input = seq[:-1] and target = seq[1:] (left-padded by
+ * target_left_pad pads: 2 for continuous_token, loader.py:189-193).  The random decisions (bar window,
+ * n_transpose, crop offset) stay with the caller, so identical decisions give identical batches.
+ * ------------------------------------------------------------------------------------- */
+#define ME_TP_MAX_PREFIX 4
+typedef struct me_token_pipeline_args {
+  int32_t B, max_events;       /* samples; row pitch (in tuples) of `events`                                   */
+  int32_t input_len;           /* loader.py:55-57: tgt_len, minus 2 for continuous_token                        */
+  int32_t target_left_pad;     /* 0, or 2 for continuous_token                                                  */
+  int32_t pad_token;
+  int32_t n_event_types, n_values; /* dims of `lut`                                                             */
+  int32_t min_pitch, max_pitch;    /* 21, 108 (data_processing.py:225)                                          */
+  int32_t _pad;
+  const int16_t* events;       /* [B, max_events, 2] (event index, value) tuples: the flattened bars            */
+  const int32_t* n_events;     /* [B] tuples per sample                                                         */
+  const int32_t* n_transpose;  /* [B] semitones, or NULL                                                        */
+  const int32_t* start;        /* [B] crop offset >= 0, or -1 when the sample starts at a bar; NULL = all -1    */
+  const int32_t* n_prefix;     /* [B] number of prefix tokens (<= ME_TP_MAX_PREFIX), or NULL                    */
+  const int32_t* prefix;       /* [B, ME_TP_MAX_PREFIX] token ids in final order                                */
+  const uint8_t* transposable; /* [n_event_types] 1 = pitched event (maps["transposable_event_inds"])           */
+  const int32_t* lut;          /* [n_event_types, n_values] tuple -> token id (maps["tuple2idx"]), -1 = none    */
+  int64_t* input;              /* out [B, input_len]                                                            */
+  int64_t* target;             /* out [B, input_len + target_left_pad], or NULL (regression: loader.py:187-188) */
+  int32_t* status;             /* out [B]: 1 when a tuple had no token id (the reference raises KeyError), or NULL */
+  void* stream;
+} me_token_pipeline_args;
+int me_token_pipeline(const me_token_pipeline_args* a);
+int me_sizeof_token_pipeline_args(void);
+
+/* ---------------------------------------------------------------------------------------
+ * Output head of the regression side model, models/music_regression.py:65-68,89 (selected by
+ * models/build_model.py:29-32): out[b, :] = tanh(Linear(d, n_out)(x[b, 0, :])) -- the first position of every
+ * sequence is pooled.  n_out <= 8 (the reference uses 2: valence, arousal).
+ *   x  T [B, Ls, d] (fp32 for ME_F32; for ME_BF16 the bf16 copy of the last LayerNorm output, the weight is
+ *      rounded to bf16 and the pre-activation / result are rounded to bf16 like the reference under autocast)
+ *   W f32 [n_out, d], bias f32 [n_out], out f32 [B, n_out]
+ * Backward: g_out f32 [B, n_out] -> dW [n_out, d], db [n_out] (written) and rows (b, 0) of d_x f32 [B, Ls, d]
+ * (the other rows are not touched: the caller zeroes d_x).
+ * ------------------------------------------------------------------------------------- */
+int me_pooled_head_forward(const void* x, int dtype, const float* W, const float* bias, int B, int Ls, int d,
+                           int n_out, float* out, void* stream);
+int me_pooled_head_backward(const float* g_out, const float* out, const void* x, int dtype, const float* W, int B,
+                            int Ls, int d, int n_out, float* dW, float* db, float* d_x, void* stream);
 
 /* ---------------------------------------------------------------------------------------
  * Optimiser step of the training loop, train.py:319-325:

@@ -7,10 +7,11 @@ Public surface (mirrors the reference's models package):
 """
 from .build_model import build_model, CONDITIONINGS  # noqa: F401
 from .transformer import MusicTransformer, positional_table, set_dropout  # noqa: F401
+from .regression import MusicRegression  # noqa: F401
 from .decode import KVCacheDecoder  # noqa: F401
 from .sampling import Sampler, generate  # noqa: F401
 from .loss import cross_entropy  # noqa: F401
 from .optim import ClipAdam  # noqa: F401
 
-__all__ = ["build_model", "MusicTransformer", "KVCacheDecoder", "Sampler", "generate", "cross_entropy", "ClipAdam", "set_dropout",
+__all__ = ["build_model", "MusicTransformer", "MusicRegression", "KVCacheDecoder", "Sampler", "generate", "cross_entropy", "ClipAdam", "set_dropout",
            "positional_table", "CONDITIONINGS"]

@@ -14,6 +14,7 @@ from . import build as _build
 ME_F32, ME_BF16 = 0, 1
 COND_MODES = {"none": 0, "discrete_token": 1, "continuous_token": 2, "continuous_concat": 3}
 ATTN_SIMT, ATTN_TENSOR = 0, 1
+ATTN_NONCAUSAL, ATTN_REF_ROUNDING = 1, 2
 EPI_BIAS, EPI_RELU, EPI_ADD_F32, EPI_RELU_MASK = 1, 2, 4, 8
 
 _vp, _i32, _i64, _f32, _u64 = C.c_void_p, C.c_int32, C.c_int64, C.c_float, C.c_uint64
@@ -23,7 +24,7 @@ class AttnArgs(C.Structure):
     _fields_ = [
         ("dtype", _i32), ("impl", _i32),
         ("B", _i32), ("H", _i32), ("Lq", _i32), ("Lk", _i32), ("dh", _i32), ("max_seq", _i32),
-        ("q_pos0", _i32), ("_pad", _i32),
+        ("q_pos0", _i32), ("flags", _i32),
         ("q", _vp), ("k", _vp), ("v", _vp), ("E", _vp),
         ("q_sb", _i64), ("q_sh", _i64), ("q_si", _i64),
         ("k_sb", _i64), ("k_sh", _i64), ("k_sj", _i64),
@@ -56,13 +57,24 @@ class SampleArgs(C.Structure):
                 ("out_probs", _vp), ("stream", _vp)]
 
 
+class TokenPipelineArgs(C.Structure):
+    _fields_ = [("B", _i32), ("max_events", _i32), ("input_len", _i32), ("target_left_pad", _i32), ("pad_token", _i32),
+                ("n_event_types", _i32), ("n_values", _i32), ("min_pitch", _i32), ("max_pitch", _i32), ("_pad", _i32),
+                ("events", _vp), ("n_events", _vp), ("n_transpose", _vp), ("start", _vp), ("n_prefix", _vp),
+                ("prefix", _vp), ("transposable", _vp), ("lut", _vp), ("input", _vp), ("target", _vp), ("status", _vp),
+                ("stream", _vp)]
+
+
+TP_MAX_PREFIX = 4
+
+
 class AdamTensor(C.Structure):
     _fields_ = [("param", _vp), ("grad", _vp), ("exp_avg", _vp), ("exp_avg_sq", _vp), ("numel", _i64)]
 
 
 class LayerArgs(C.Structure):
     _fields_ = [
-        ("dtype", _i32), ("attn_impl", _i32), ("training", _i32), ("_pad0", _i32),
+        ("dtype", _i32), ("attn_impl", _i32), ("training", _i32), ("attn_flags", _i32),
         ("B", _i32), ("Ls", _i32), ("d", _i32), ("H", _i32), ("d_inner", _i32), ("max_seq", _i32),
         ("dropout_p", _f32), ("ln_eps", _f32), ("seed", _u64),
     ] + [(n, _vp) for n in _LAYER_PTRS]
@@ -111,6 +123,11 @@ _PROTOS = {
     "me_colsum_ws": (C.c_int, [_vp, C.c_int, C.c_int, C.c_int, C.c_int, _vp, _vp, C.c_int64, _vp]),
     "me_convert_2d": (C.c_int, [_vp, C.c_int, C.c_int, _vp, C.c_int, C.c_int, C.c_int, C.c_int, _vp]),
     "me_convert_batched": (C.c_int, [_vp, C.c_int, _vp]),
+    "me_token_pipeline": (C.c_int, [C.POINTER(TokenPipelineArgs)]),
+    "me_sizeof_token_pipeline_args": (C.c_int, []),
+    "me_pooled_head_forward": (C.c_int, [_vp, C.c_int, _vp, _vp, C.c_int, C.c_int, C.c_int, C.c_int, _vp, _vp]),
+    "me_pooled_head_backward": (C.c_int, [_vp, _vp, _vp, C.c_int, _vp, C.c_int, C.c_int, C.c_int, C.c_int, _vp, _vp,
+                                          _vp, _vp]),
     "me_attention_forward": (C.c_int, [C.POINTER(AttnArgs)]),
     "me_attention_backward": (C.c_int, [C.POINTER(AttnBwdArgs)]),
     "me_attention_backward_workspace_floats": (C.c_int64, [C.c_int] * 5),
@@ -167,7 +184,8 @@ def load(build_if_missing: bool = True):
                 fn.argtypes = args
         for cname, st in (("me_sizeof_attn_args", AttnArgs), ("me_sizeof_attn_bwd_args", AttnBwdArgs),
                           ("me_sizeof_layer_args", LayerArgs), ("me_sizeof_layer_bwd_args", LayerBwdArgs),
-                          ("me_sizeof_decode_layer_args", DecodeLayerArgs), ("me_sizeof_sample_args", SampleArgs)):
+                          ("me_sizeof_decode_layer_args", DecodeLayerArgs), ("me_sizeof_sample_args", SampleArgs),
+                          ("me_sizeof_token_pipeline_args", TokenPipelineArgs)):
             if getattr(lib, cname)() != C.sizeof(st):
                 raise RuntimeError(f"midi_emotion_b200: struct mirror {st.__name__} does not match the library")
         _lib = lib

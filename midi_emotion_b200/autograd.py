@@ -34,6 +34,7 @@ class _Acts:
 def _layer_args(model, wl: dict, lay, act: dict, x_f32, x_T, keypad, a: _Acts, layer_idx: int) -> _lib.LayerArgs:
     la = _lib.LayerArgs()
     la.dtype, la.attn_impl, la.training = a.dtype, a.attn_impl, 1 if a.training else 0
+    la.attn_flags = model._attn_flags()
     la.B, la.Ls, la.d, la.H = a.B, a.Ls, model.embedding_dim, model.num_head
     la.d_inner, la.max_seq = model.d_inner, model.max_seq
     la.dropout_p, la.ln_eps = a.p, 1e-6
@@ -52,11 +53,12 @@ def _layer_args(model, wl: dict, lay, act: dict, x_f32, x_T, keypad, a: _Acts, l
 
 
 def run_forward(model, tokens: torch.Tensor, cond: Optional[torch.Tensor], need_grad: bool, dtype=None,
-                kv_sink=None, last_only: bool = False):
+                kv_sink=None, last_only: bool = False, head: bool = True):
     """Enqueue the forward pass.  Returns (logits_padded [M, Vp] in compute type, acts).
 
     kv_sink(layer_index, qkv[M, 3d]) is called after every layer (KV-cache prefill);
-    last_only computes the output head for the last position of every sequence only ([B, Vp])."""
+    last_only computes the output head for the last position of every sequence only ([B, Vp]);
+    head=False stops after the encoder stack (the regression model pools it itself) and returns (None, acts)."""
     if dtype is None:
         dtype = model._resolve_dtype()
     tdt = _tdtype(dtype)
@@ -89,6 +91,7 @@ def run_forward(model, tokens: torch.Tensor, cond: Optional[torch.Tensor], need_
 
     a.layers = []
     x_f32, x_T = a.x_f32, a.x_T
+    keypad = a.keypad if model.use_keypad else None
     scratch = None
     for l, lay in enumerate(model.enc_layers):
         if need_grad or scratch is None:
@@ -108,7 +111,7 @@ def run_forward(model, tokens: torch.Tensor, cond: Optional[torch.Tensor], need_
         act["out2_f32"] = torch.empty(M, d, **f32)
         act["out2_T"] = act["out2_f32"] if dtype == ME_F32 else torch.empty(M, d, **tt)
         act["x_f32"], act["x_T"] = x_f32, x_T
-        la = _layer_args(model, wc["layers"][l], lay, act, x_f32, x_T, a.keypad, a, l)
+        la = _layer_args(model, wc["layers"][l], lay, act, x_f32, x_T, keypad, a, l)
         if need_grad:
             la.training = 1  # keep the statistics needed by backward even when dropout is off
             la.dropout_p = a.p
@@ -121,6 +124,8 @@ def run_forward(model, tokens: torch.Tensor, cond: Optional[torch.Tensor], need_
             a.layers.append(act)
     if not need_grad:
         a.layers.append({"out2_T": x_T, "out2_f32": x_f32})
+    if not head:
+        return None, a
 
     # output head (music_multi.py:106): logits[M, V]; rows padded to Vp so that they stay 16-byte aligned
     Vp = (V + 7) // 8 * 8
@@ -170,17 +175,7 @@ def run_backward(model, tokens, cond, a: _Acts, g_logits: torch.Tensor, ld_g: Op
     grads = {}
 
     hook = getattr(model, "_grad_ready_hook", None)
-
-    def group(shapes):
-        """One flat fp32 buffer carved into gradient tensors (a data-parallel wrapper reduces it in one call)."""
-        sizes = [int(torch.Size(sh).numel()) for sh in shapes.values()]
-        padded = [(n + 3) // 4 * 4 for n in sizes]           # keep every tensor 16-byte aligned
-        flat = torch.empty(sum(padded), **f32)
-        out, off = {}, 0
-        for (name, sh), n, pn in zip(shapes.items(), sizes, padded):
-            out[name] = flat[off:off + n].view(sh)
-            off += pn
-        return flat, out
+    group = _grouper(dev)
 
     last = a.layers[-1]
     # head: dW = g^T x, db = colsum(g), dx = g W
@@ -202,6 +197,43 @@ def run_backward(model, tokens, cond, a: _Acts, g_logits: torch.Tensor, ld_g: Op
                   None, 0, stream)
     if hook is not None:
         hook(flat_head)
+    backward_stack(model, tokens, cond, a, d_x, grads)
+    return [grads[n] for n, _ in model.named_parameters()]
+
+
+def _grouper(dev):
+    f32 = dict(device=dev, dtype=torch.float32)
+
+    def group(shapes):
+        """One flat fp32 buffer carved into gradient tensors (a data-parallel wrapper reduces it in one call)."""
+        sizes = [int(torch.Size(sh).numel()) for sh in shapes.values()]
+        padded = [(n + 3) // 4 * 4 for n in sizes]           # keep every tensor 16-byte aligned
+        flat = torch.empty(sum(padded), **f32)
+        out, off = {}, 0
+        for (name, sh), n, pn in zip(shapes.items(), sizes, padded):
+            out[name] = flat[off:off + n].view(sh)
+            off += pn
+        return flat, out
+
+    return group
+
+
+def backward_stack(model, tokens, cond, a: _Acts, d_x: torch.Tensor, grads: dict) -> None:
+    """Backward of the encoder layers and the input stage.  d_x: fp32 [M, d] gradient w.r.t. the output of the last
+    layer (overwritten).  Fills `grads` (parameter name -> fp32 gradient)."""
+    dtype = a.dtype
+    tdt = _tdtype(dtype)
+    dev = tokens.device
+    B, L, Ls, M = a.B, a.L, a.Ls, a.M
+    d, di, H, V = model.embedding_dim, model.d_inner, model.num_head, model.vocab_size
+    dh = d // H
+    wc = model._weights(dtype)
+    stream = _stream()
+    f32 = dict(device=dev, dtype=torch.float32)
+    tt = dict(device=dev, dtype=tdt)
+    hook = getattr(model, "_grad_ready_hook", None)
+    group = _grouper(dev)
+    keypad = a.keypad if model.use_keypad else None
 
     ws = {
         "g_a": torch.empty(M, d, **f32), "g_b": torch.empty(M, d, **f32), "g_T": torch.empty(M, d, **tt),
@@ -229,7 +261,7 @@ def run_backward(model, tokens, cond, a: _Acts, g_logits: torch.Tensor, ld_g: Op
         })
         dWqkv, dbqkv = g["dWqkv"], g["dbqkv"]
         ba = _lib.LayerBwdArgs()
-        ba.f = _layer_args(model, wc["layers"][l], lay, act, act["x_f32"], act["x_T"], a.keypad, a, l)
+        ba.f = _layer_args(model, wc["layers"][l], lay, act, act["x_f32"], act["x_T"], keypad, a, l)
         ba.f.training = 1
         ba.d_out, ba.d_x = ptr(d_x), ptr(d_x)
         for k, t in g.items():
@@ -278,7 +310,6 @@ def run_backward(model, tokens, cond, a: _Acts, g_logits: torch.Tensor, ld_g: Op
         grads["fc_condition.1.weight"], grads["fc_condition.1.bias"] = d_c[2], d_c[3]
     elif model.d_condition > 0:
         grads["fc_condition.weight"], grads["fc_condition.bias"] = d_c[0], d_c[1]
-    return [grads[n] for n, _ in model.named_parameters()]
 
 
 class _ModelFn(torch.autograd.Function):

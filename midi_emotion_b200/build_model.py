@@ -21,16 +21,21 @@ def build_model(args, load_config_dict=None):
         raise ValueError("build_model needs an args dict or a load_config_dict")
     if "regression" not in args:
         args["regression"] = False
-    if args["regression"]:
-        # models/music_regression.py is outside the accelerated hot path
-        raise NotImplementedError("midi_emotion_b200: the regression model is not part of the B200 hot path")
     conditioning = args["conditioning"]
-    if conditioning not in CONDITIONINGS:
-        raise ValueError(f"unknown conditioning {conditioning!r}; expected one of {CONDITIONINGS}")
-    model = MusicTransformer(
-        embedding_dim=args["d_model"], d_inner=args["d_inner"], d_condition=args["d_condition"],
-        vocab_size=args["vocab_size"], num_layer=args["n_layer"], num_head=args["n_head"], max_seq=MAX_SEQ,
-        dropout=args["dropout"], pad_token=0, continuous_token=(conditioning == "continuous_token"))
+    if args["regression"]:
+        # models/build_model.py:29-32: MusicRegression with output_size 2 (it asserts d_condition <= 0)
+        from .regression import MusicRegression
+        model = MusicRegression(
+            embedding_dim=args["d_model"], d_inner=args["d_inner"], d_condition=args["d_condition"],
+            vocab_size=args["vocab_size"], num_layer=args["n_layer"], num_head=args["n_head"], max_seq=MAX_SEQ,
+            dropout=args["dropout"], pad_token=0, output_size=2)
+    else:
+        if conditioning not in CONDITIONINGS:
+            raise ValueError(f"unknown conditioning {conditioning!r}; expected one of {CONDITIONINGS}")
+        model = MusicTransformer(
+            embedding_dim=args["d_model"], d_inner=args["d_inner"], d_condition=args["d_condition"],
+            vocab_size=args["vocab_size"], num_layer=args["n_layer"], num_head=args["n_head"], max_seq=MAX_SEQ,
+            dropout=args["dropout"], pad_token=0, continuous_token=(conditioning == "continuous_token"))
     if load_config_dict is not None and args["overwrite_dropout"]:
         set_dropout(model, args["dropout"])
         print(f"Dropout rate changed to {args['dropout']}")

@@ -1,5 +1,7 @@
 // Relative global attention on CUDA cores, fp32 arithmetic, any storage dtype.
 //   S[i,j] = (q_i.k_j + q_i.E[max_seq-1-(i-j)]) / sqrt(dh)   for j <= i and key j not pad
+// (ME_ATTN_NONCAUSAL: every key j < Lk is visible and the E term exists for j <= i only -- the
+//  regression side model, models/music_regression.py:78,256-262)
 // This is (a) the fp32 parity path, (b) the decode-step attention over the KV cache (one query
 // row per sequence, HBM-bound: it streams the cache once), (c) the correctness reference that the
 // tensor-core attention kernels are tested against on the device.
@@ -36,7 +38,7 @@ __device__ __forceinline__ float dot_row<bf16>(const float* __restrict__ qs, con
 }
 
 struct AttnP {
-  int B, H, Lq, Lk, dh, max_seq, q_pos0;
+  int B, H, Lq, Lk, dh, max_seq, q_pos0, noncausal;
   int64_t q_sb, q_sh, q_si, k_sb, k_sh, k_sj, v_sb, v_sh, v_sj, o_sb, o_si, keypad_ld;
   const int32_t* pos_dev;
 };
@@ -70,13 +72,14 @@ attn_fwd_simt(const T* __restrict__ q, const T* __restrict__ k, const T* __restr
 #pragma unroll
   for (int c = 0; c < AT_MAX_DH / 32; ++c) acc[c] = 0.f;
 
-  for (int j0 = 0; j0 <= i; j0 += 32) {
+  const int jend = p.noncausal ? (p.pos_dev ? i + 1 : p.Lk) : i + 1;  // keys 0 .. jend-1 can be visible
+  for (int j0 = 0; j0 < jend; j0 += 32) {
     const int j = j0 + lane;
-    const bool valid = (j <= i) && !(kp && kp[j]);
+    const bool valid = (j < jend) && !(kp && kp[j]);
     float s = -INFINITY;
     if (valid) {
       const float qk = dot_row<T>(qs, kb + j * p.k_sj, dh);
-      const float qe = dot_row<T>(qs, E + static_cast<int64_t>(p.max_seq - 1 - (i - j)) * dh, dh);
+      const float qe = j <= i ? dot_row<T>(qs, E + static_cast<int64_t>(p.max_seq - 1 - (i - j)) * dh, dh) : 0.f;
       s = (qk + qe) / sqrt_dh;
     }
     const float cm = warp_max(s);
@@ -87,7 +90,7 @@ attn_fwd_simt(const T* __restrict__ q, const T* __restrict__ k, const T* __restr
     l = l * alpha + warp_sum(pj);
 #pragma unroll
     for (int c = 0; c < AT_MAX_DH / 32; ++c) acc[c] *= alpha;
-    const int jn = min(32, i - j0 + 1);
+    const int jn = min(32, jend - j0);
     for (int jj = 0; jj < jn; ++jj) {
       const float pb = __shfl_sync(0xffffffffu, pj, jj);
       if (pb != 0.f) {
@@ -152,31 +155,40 @@ attn_bwd_dq_simt(const T* __restrict__ q, const T* __restrict__ k, const T* __re
 #pragma unroll
   for (int c = 0; c < AT_MAX_DH / 32; ++c) acc[c] = 0.f;
 
-  for (int j0 = 0; j0 <= i; j0 += 32) {
+  const int jend = p.noncausal ? p.Lk : i + 1;
+  for (int j0 = 0; j0 < jend; j0 += 32) {
     const int j = j0 + lane;
-    const bool valid = (j <= i) && !(kp && kp[j]) && lse_i != -INFINITY;
+    const bool valid = (j < jend) && !(kp && kp[j]) && lse_i != -INFINITY;
     float ds = 0.f;
     if (valid) {
       const float qk = dot_row<T>(qs, kb + j * p.k_sj, dh);
-      const float qe = dot_row<T>(qs, E + static_cast<int64_t>(p.max_seq - 1 - (i - j)) * dh, dh);
+      const float qe = j <= i ? dot_row<T>(qs, E + static_cast<int64_t>(p.max_seq - 1 - (i - j)) * dh, dh) : 0.f;
       const float s = (qk + qe) / sqrt_dh;
       const float pj = expf(s - lse_i);
       const float dp = dot_row<T>(dos, vb + j * p.v_sj, dh);
       ds = pj * (dp - Di) / sqrt_dh;
     }
-    const int jn = min(32, i - j0 + 1);
+    const int jn = min(32, jend - j0);
     for (int jj = 0; jj < jn; ++jj) {
       const float dsb = __shfl_sync(0xffffffffu, ds, jj);
       if (dsb != 0.f) {
         const int jx = j0 + jj;
         const T* krow = kb + jx * p.k_sj;
-        const int64_t eidx = static_cast<int64_t>(p.max_seq - 1 - (i - jx)) * dh;
+        if (jx <= i) {
+          const int64_t eidx = static_cast<int64_t>(p.max_seq - 1 - (i - jx)) * dh;
 #pragma unroll
-        for (int c = 0; c < AT_MAX_DH / 32; ++c) {
-          const int e = lane + 32 * c;
-          if (e < dh) {
-            acc[c] = fmaf(dsb, to_f32<T>(krow[e]) + to_f32<T>(E[eidx + e]), acc[c]);
-            atomicAdd(&dE[eidx + e], dsb * qs[e]);
+          for (int c = 0; c < AT_MAX_DH / 32; ++c) {
+            const int e = lane + 32 * c;
+            if (e < dh) {
+              acc[c] = fmaf(dsb, to_f32<T>(krow[e]) + to_f32<T>(E[eidx + e]), acc[c]);
+              atomicAdd(&dE[eidx + e], dsb * qs[e]);
+            }
+          }
+        } else {  // above the diagonal (non-causal only): no relative term
+#pragma unroll
+          for (int c = 0; c < AT_MAX_DH / 32; ++c) {
+            const int e = lane + 32 * c;
+            if (e < dh) acc[c] = fmaf(dsb, to_f32<T>(krow[e]), acc[c]);
           }
         }
       }
@@ -224,7 +236,7 @@ attn_bwd_dkv_simt(const T* __restrict__ q, const T* __restrict__ k, const T* __r
   for (int c = 0; c < AT_MAX_DH / 32; ++c) acck[c] = accv[c] = 0.f;
 
   if (!key_masked) {
-    for (int i0 = j; i0 < p.Lq; i0 += 32) {
+    for (int i0 = p.noncausal ? 0 : j; i0 < p.Lq; i0 += 32) {
       const int i = i0 + lane;
       float pj = 0.f, ds = 0.f;
       if (i < p.Lq) {
@@ -234,7 +246,8 @@ attn_bwd_dkv_simt(const T* __restrict__ q, const T* __restrict__ k, const T* __r
           const T* qrow = qb + i * p.q_si;
           // q_i . k_j and q_i . E[idx]: dot_row wants the fp32 vector first
           float qk = 0.f, qe = 0.f, dp = 0.f;
-          const T* erow = E + static_cast<int64_t>(p.max_seq - 1 - (i - j)) * dh;
+          const bool rel = i >= j;  // the relative term is lower-triangular
+          const T* erow = E + static_cast<int64_t>(p.max_seq - 1 - (rel ? i - j : 0)) * dh;
           const T* dorow = dob + b * 0 + i * p.o_si;
           for (int c = 0; c < dh; ++c) {
             const float qv = to_f32<T>(qrow[c]);
@@ -242,6 +255,7 @@ attn_bwd_dkv_simt(const T* __restrict__ q, const T* __restrict__ k, const T* __r
             qe = fmaf(qv, to_f32<T>(erow[c]), qe);
             dp = fmaf(to_f32<T>(dorow[c]), vs[c], dp);
           }
+          if (!rel) qe = 0.f;
           const float s = (qk + qe) / sqrt_dh;
           pj = expf(s - lse_i);
           ds = pj * (dp - dsum[row_id]) / sqrt_dh;
@@ -285,6 +299,7 @@ static AttnP to_p(const me_attn_args* a) {
   p.k_sb = a->k_sb; p.k_sh = a->k_sh; p.k_sj = a->k_sj;
   p.v_sb = a->v_sb; p.v_sh = a->v_sh; p.v_sj = a->v_sj;
   p.o_sb = a->o_sb; p.o_si = a->o_si; p.keypad_ld = a->keypad_ld; p.pos_dev = a->pos_dev;
+  p.noncausal = (a->flags & ME_ATTN_NONCAUSAL) ? 1 : 0;
   return p;
 }
 

@@ -42,9 +42,16 @@ struct FaParams {
   bf16* out;
   float* lse;
   float scale_log2;  // log2(e) / sqrt(dh)
+  float sqrt_dh;
+  int noncausal;     // ME_ATTN_NONCAUSAL: every key < L is visible (the band of E zero-fills itself above the diagonal)
 };
 
-template <int DH>
+// fp32 value rounded to the nearest bf16 (the reference's rounding points under autocast)
+__device__ __forceinline__ float bf16r(float x) { return __bfloat162float(__float2bfloat16_rn(x)); }
+
+// RR = ME_ATTN_REF_ROUNDING: QK^T, Srel, their sum and the scaled logits are rounded to bf16 where the reference
+// rounds them under autocast (music_multi.py:215-222: einsum -> bf16, matmul -> bf16, bf16 + bf16, bf16 / sqrt(dh)).
+template <int DH, bool RR>
 __global__ void __launch_bounds__(FA_THREADS, 2)
 attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                    const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmE, FaParams p) {
@@ -64,7 +71,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   const int qi = gridDim.x - 1 - blockIdx.x;  // heavy (late) query tiles first
   const int h = blockIdx.y, b = blockIdx.z;
   const int i0 = qi * FA_BM;
-  const int kmax = min(i0 + FA_BM, p.L);       // keys 0 .. kmax-1 can be visible
+  const int kmax = p.noncausal ? p.L : min(i0 + FA_BM, p.L);  // keys 0 .. kmax-1 can be visible
   const int nt = (kmax + FA_BN - 1) / FA_BN;
 
   // Thread 0 is also the TMA producer and the MMA issuer: the per-tile schedule is a strict sequence
@@ -119,7 +126,9 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
 #pragma unroll
   for (int c = 0; c < DH; ++c) O[c] = 0.f;
   float m = -INFINITY, l = 0.f;
-  const float cs = p.scale_log2;
+  // RR: x is already divided by sqrt(dh) (and rounded), only log2(e) remains
+  const float cs = RR ? 1.4426950408889634f : p.scale_log2;
+  const bool any_kp = kp != nullptr || p.noncausal;
 
   for (int t = 0; t < nt; ++t) {
     const int s = t & 1;
@@ -144,12 +153,12 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
 
     const int j0 = t * FA_BN;
     uint32_t kp0 = 0, kp1 = 0;
-    if (kp) {
+    if (any_kp) {  // (keys past the sequence only matter without the causal predicate)
       const int ja = j0 + lane, jb = j0 + 32 + lane;
-      kp0 = __ballot_sync(0xffffffffu, ja < p.L && kp[ja] != 0);
-      kp1 = __ballot_sync(0xffffffffu, jb < p.L && kp[jb] != 0);
+      kp0 = __ballot_sync(0xffffffffu, ja >= p.L || (kp && kp[ja] != 0));
+      kp1 = __ballot_sync(0xffffffffu, jb >= p.L || (kp && kp[jb] != 0));
     }
-    const int lim = i - j0;  // columns b <= lim are causal-visible
+    const int lim = p.noncausal ? 63 : i - j0;  // columns b <= lim are causal-visible
     uint32_t v0 = lim >= 31 ? 0xffffffffu : (lim < 0 ? 0u : ((2u << lim) - 1u));
     uint32_t v1 = lim >= 63 ? 0xffffffffu : (lim < 32 ? 0u : ((2u << (lim - 32)) - 1u));
     v0 &= ~kp0;
@@ -167,7 +176,12 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       tc_wait_ld();
       skew_select(rv, shift);
 #pragma unroll
-      for (int bb = 0; bb < 32; ++bb) x0[bb] = __uint_as_float(sv[bb]) + __uint_as_float(rv[bb]);
+      for (int bb = 0; bb < 32; ++bb) {
+        if (RR)
+          x0[bb] = bf16r(__fdiv_rn(bf16r(bf16r(__uint_as_float(sv[bb])) + bf16r(__uint_as_float(rv[bb]))), p.sqrt_dh));
+        else
+          x0[bb] = __uint_as_float(sv[bb]) + __uint_as_float(rv[bb]);
+      }
     }
     {
       uint32_t sv[32], rv[64];
@@ -176,7 +190,12 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       tc_wait_ld();
       skew_select(rv, shift);
 #pragma unroll
-      for (int bb = 0; bb < 32; ++bb) x1[bb] = __uint_as_float(sv[bb]) + __uint_as_float(rv[bb]);
+      for (int bb = 0; bb < 32; ++bb) {
+        if (RR)
+          x1[bb] = bf16r(__fdiv_rn(bf16r(bf16r(__uint_as_float(sv[bb])) + bf16r(__uint_as_float(rv[bb]))), p.sqrt_dh));
+        else
+          x1[bb] = __uint_as_float(sv[bb]) + __uint_as_float(rv[bb]);
+      }
     }
     if (need_mask) {
 #pragma unroll
@@ -270,10 +289,10 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   }
 }
 
-template <int DH>
+template <int DH, bool RR>
 static int launch_fwd(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const CUtensorMap& te,
                       const FaParams& p, dim3 grid, cudaStream_t st) {
-  auto kern = attn_fwd_tc_kernel<DH>;
+  auto kern = attn_fwd_tc_kernel<DH, RR>;
   static bool configured = false;
   if (!configured) {
     ME_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, FA_SMEM));
@@ -310,12 +329,19 @@ int launch_attn_fwd_tc(const me_attn_args* a) {
   p.o_sb = a->o_sb; p.o_si = a->o_si; p.keypad_ld = a->keypad_ld; p.keypad = a->keypad;
   p.out = static_cast<bf16*>(a->out);
   p.lse = a->lse;
-  p.scale_log2 = 1.4426950408889634f / sqrtf(static_cast<float>(a->dh));
+  p.sqrt_dh = sqrtf(static_cast<float>(a->dh));
+  p.scale_log2 = 1.4426950408889634f / p.sqrt_dh;
+  p.noncausal = (a->flags & ME_ATTN_NONCAUSAL) ? 1 : 0;
   dim3 grid((a->Lq + FA_BM - 1) / FA_BM, a->H, a->B);
   cudaStream_t st = static_cast<cudaStream_t>(a->stream);
-  if (a->dh == 64) return launch_fwd<64>(tq, tk, tv, te, p, grid, st);
-  if (a->dh == 48) return launch_fwd<48>(tq, tk, tv, te, p, grid, st);
-  return launch_fwd<32>(tq, tk, tv, te, p, grid, st);
+  if (a->flags & ME_ATTN_REF_ROUNDING) {
+    if (a->dh == 64) return launch_fwd<64, true>(tq, tk, tv, te, p, grid, st);
+    if (a->dh == 48) return launch_fwd<48, true>(tq, tk, tv, te, p, grid, st);
+    return launch_fwd<32, true>(tq, tk, tv, te, p, grid, st);
+  }
+  if (a->dh == 64) return launch_fwd<64, false>(tq, tk, tv, te, p, grid, st);
+  if (a->dh == 48) return launch_fwd<48, false>(tq, tk, tv, te, p, grid, st);
+  return launch_fwd<32, false>(tq, tk, tv, te, p, grid, st);
 }
 
 }  // namespace me

@@ -64,6 +64,7 @@ struct FbParams {
   bf16* dk;
   bf16* dv;
   float scale_log2, scale;
+  int noncausal;     // ME_ATTN_NONCAUSAL: every query tile, every key < L visible
   long long* trace;  // debugging: per-phase clock64() stamps of one CTA (me_debug_trace_set), else NULL
 };
 static long long* g_attn_bwd_trace = nullptr;
@@ -170,7 +171,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   const int kt = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
   const int j0 = kt * FB_BN;
   const int nq = (p.L + FB_BM - 1) / FB_BM;
-  const int qi0 = j0 / FB_BM;
+  const int qi0 = p.noncausal ? 0 : j0 / FB_BM;
   const int nsteps = nq - qi0;
   // consecutive block ids (the CTAs resident at the same time) accumulate dE into different copies
   float* const dE_mine =
@@ -381,9 +382,9 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     const uint32_t t_lane = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16);
     const uint8_t* kp = p.keypad ? p.keypad + static_cast<int64_t>(b) * p.keypad_ld : nullptr;
     uint32_t kpm = 0;  // key-pad bits of this thread's 32 keys
-    if (kp) {
+    if (kp || p.noncausal) {  // (keys past the sequence only matter without the causal predicate)
       const int j = j0 + 32 * half + lane;
-      kpm = __ballot_sync(0xffffffffu, j < p.L && kp[j] != 0);
+      kpm = __ballot_sync(0xffffffffu, j >= p.L || (kp && kp[j] != 0));
     }
     const float cs = p.scale_log2;
     // this thread's 32 values sit at band columns c = 127 - a + 32*half + bb
@@ -401,7 +402,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         l_nat = p.lse[stat];
         Di = p.dsum[stat];
       }
-      const int lim = i - j0 - 32 * half;  // this thread's columns bb <= lim are causal-visible
+      const int lim = p.noncausal ? 31 : i - j0 - 32 * half;  // this thread's columns bb <= lim are causal-visible
       uint32_t vm = lim >= 31 ? 0xffffffffu : (lim < 0 ? 0u : ((2u << lim) - 1u));
       vm &= ~kpm;
 
@@ -720,6 +721,7 @@ int launch_attn_bwd_tc(const me_attn_bwd_args* ba) {
   p.dk = static_cast<bf16*>(ba->dk); p.dv = static_cast<bf16*>(ba->dv);
   p.scale = 1.f / sqrtf(static_cast<float>(dh));
   p.scale_log2 = 1.4426950408889634f * p.scale;
+  p.noncausal = (a->flags & ME_ATTN_NONCAUSAL) ? 1 : 0;
   p.trace = g_attn_bwd_trace;
   dim3 grid((L + FB_BN - 1) / FB_BN, H, B);
   int rc;

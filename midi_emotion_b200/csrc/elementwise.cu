@@ -56,14 +56,18 @@ __global__ void embed_fwd_kernel(const int64_t* __restrict__ tokens, const float
   const float* perow = pe + static_cast<int64_t>(pos) * d;
   for (int c = threadIdx.x; c < d; c += blockDim.x) {
     float v;
+    // bf16 path: the condition Linears run under autocast in the reference (inputs, weights and bias cast to
+    // bf16, bf16 result), while the embedding lookup, its scale and the positional add stay fp32
+    constexpr bool lowp = sizeof(T) == 2;
+    auto rb = [](float x) { return lowp ? __bfloat162float(__float2bfloat16_rn(x)) : x; };
     if (prefix) {
       // Linear(1, d): cond[b, s] * w[c, 0] + bias[c]
-      v = (s == 0) ? fmaf(c0, cw0[c], cb0[c]) : fmaf(c1, cw1[c], cb1[c]);
+      v = (s == 0) ? rb(fmaf(rb(c0), rb(cw0[c]), rb(cb0[c]))) : rb(fmaf(rb(c1), rb(cw1[c]), rb(cb1[c])));
     } else if (c < de) {
       v = tok_ok ? emb_w[tok * de + c] * scale : 0.f;
     } else {
       const int j = c - de;  // Linear(2, dc)
-      v = cb0[j] + (c0 * cw0[j * 2 + 0] + c1 * cw0[j * 2 + 1]);
+      v = rb(rb(cb0[j]) + (rb(c0) * rb(cw0[j * 2 + 0]) + rb(c1) * rb(cw0[j * 2 + 1])));
     }
     v += perow[c];
     v *= dropout_scale(p, inv_keep, seed, static_cast<uint64_t>(out_row) * d + c);

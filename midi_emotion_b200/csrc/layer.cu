@@ -62,6 +62,7 @@ static void fill_attn(const me_layer_args* a, me_attn_args* t) {
   memset(t, 0, sizeof(*t));
   t->dtype = a->dtype;
   t->impl = a->attn_impl;
+  t->flags = a->attn_flags;
   t->B = a->B; t->H = a->H; t->Lq = a->Ls; t->Lk = a->Ls; t->dh = dh; t->max_seq = a->max_seq; t->q_pos0 = 0;
   t->q = a->qkv;
   t->k = offs(static_cast<const void*>(a->qkv), a->dtype, d);

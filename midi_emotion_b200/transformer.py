@@ -7,9 +7,10 @@ MusicTransformerContinuousToken) with the arithmetic done by the sm_100a kernels
 * No arithmetic happens in PyTorch: `forward` enqueues the C-ABI calls on the current CUDA stream;
   `backward` is hand-derived (one `torch.autograd.Function` around the whole model) so that
   `loss.backward()`, `clip_grad_norm_`, `optim.Adam` and DDP-style hooks see ordinary parameters.
-* Precision follows the caller the way the reference does: under `torch.autocast(..., bfloat16)`
-  (train.py:281, generate.py:116) the bf16 tensor-core path runs, otherwise the exact fp32 path.
-  `model.precision = "bf16" | "fp32"` overrides.
+* Precision follows the caller the way the reference does: under autocast the bf16 tensor-core path runs,
+  otherwise the exact fp32 path.  The reference's own call sites (train.py:281, generate.py:116) use
+  `torch.cuda.amp.autocast`, i.e. float16 + GradScaler: that is accepted and computed in bf16 (logits are
+  returned as bfloat16; the scaler's loss scale passes through the linear backward unchanged).  `model.precision = "bf16" | "fp32"` overrides.
 * CUDA only.  A CPU tensor, a missing library or an unsupported shape raises; nothing falls back.
 """
 from __future__ import annotations
@@ -93,6 +94,12 @@ class MusicTransformer(nn.Module):
         self.dropout_p = float(dropout)
         self.precision = "auto"        # "auto" (follow torch autocast) | "fp32" | "bf16"
         self.attn_impl = "auto"        # "auto" | "simt" | "tensor"
+        self.causal = True             # False: models/music_regression.py (no mask at all)
+        self.use_keypad = True         # key-pad part of generate_mask (music_multi.py:25-38)
+        self._vocab_head = True        # fc = Linear(d, V) applied to every position
+        # True: the tensor-core attention rounds QK^T, Srel, their sum and the scaled logits to bf16 exactly where
+        # the reference does under autocast (music_multi.py:215-222); default keeps them in fp32
+        self.reference_rounding = False
 
         self.embedding = nn.Embedding(vocab_size, embedding_dim - d_condition, padding_idx=pad_token)
         if self.continuous_token:
@@ -144,8 +151,23 @@ class MusicTransformer(nn.Module):
             adt = torch.get_autocast_dtype("cuda")
             if adt == torch.bfloat16:
                 return ME_BF16
-            raise RuntimeError("midi_emotion_b200: only bfloat16 autocast is supported (B200 path computes in bf16)")
+            if adt == torch.float16:
+                # train.py:281 / generate.py:116 call `torch.cuda.amp.autocast(enabled=amp)`, i.e. fp16 autocast with
+                # a GradScaler (train.py:108).  The B200 path computes in bf16 (same tensor-core rate, fp32 exponent
+                # range): it runs here unchanged (logits come back as bf16); the GradScaler's loss scale passes
+                # through the backward linearly, the fp32 parameter gradients are unscaled by scaler.unscale_().
+                global _WARNED_FP16
+                if not _WARNED_FP16:
+                    _WARNED_FP16 = True
+                    import warnings
+                    warnings.warn("midi_emotion_b200: float16 autocast requested; the B200 kernels compute in bfloat16 "
+                                  "(logits are returned as bfloat16)", stacklevel=3)
+                return ME_BF16
+            raise RuntimeError(f"midi_emotion_b200: unsupported autocast dtype {adt}")
         return ME_F32
+
+    def _attn_flags(self) -> int:
+        return (0 if self.causal else _lib.ATTN_NONCAUSAL) | (_lib.ATTN_REF_ROUNDING if self.reference_rounding else 0)
 
     def _resolve_attn(self, dtype: int) -> int:
         if self.attn_impl == "simt":
@@ -188,7 +210,8 @@ class MusicTransformer(nn.Module):
                     "W1": torch.empty(di, d, device=dev, dtype=tdt),
                     "W2": torch.empty(d, di, device=dev, dtype=tdt),
                 })
-            wc["Wfc"] = torch.empty(V, d, device=dev, dtype=tdt)
+            if self._vocab_head:
+                wc["Wfc"] = torch.empty(V, d, device=dev, dtype=tdt)
             # table of (fp32 parameter -> compute-type copy) pairs for me_convert_batched
             entries = []
 
@@ -207,7 +230,8 @@ class MusicTransformer(nn.Module):
                 add(w["Wo"], lay.rga.fc.weight, dtype)
                 add(w["W1"], lay.FFN_pre.weight, dtype)
                 add(w["W2"], lay.FFN_suf.weight, dtype)
-            add(wc["Wfc"], self.fc.weight, dtype)
+            if self._vocab_head:
+                add(wc["Wfc"], self.fc.weight, dtype)
             table = (_lib.ConvertDesc * len(entries))(*[_lib.ConvertDesc(*e) for e in entries])
             raw = torch.frombuffer(bytearray(bytes(table)), dtype=torch.uint8)
             wc["table"] = raw.to(dev)
@@ -256,6 +280,7 @@ class MusicTransformer(nn.Module):
 
 
 _TENSOR_ATTENTION_AVAILABLE = True
+_WARNED_FP16 = False
 
 
 def set_dropout(model: MusicTransformer, rate: float) -> MusicTransformer:

@@ -60,8 +60,10 @@ def test_build_model_load_config_dict_contract():
     assert model.dropout_p == pytest.approx(0.3)
     with pytest.raises(KeyError):
         build_model(None, load_config_dict={k: v for k, v in cfg.items() if k != "overwrite_dropout"})
-    with pytest.raises(NotImplementedError):
+    with pytest.raises(AssertionError):       # models/music_regression.py:42: `assert d_condition <= 0`
         build_model(dict(cfg, regression=True))
+    reg, _ = build_model(dict(cfg, regression=True, d_condition=-1, conditioning="none"))   # build_model.py:29-32
+    assert type(reg).__name__ == "MusicRegression" and {"fc.0.weight", "fc.0.bias"} <= set(reg.state_dict())
 
 
 def test_positional_table_matches_reference_rows():
