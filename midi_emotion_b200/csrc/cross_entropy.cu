@@ -13,11 +13,16 @@ namespace me {
 constexpr int CE_WARPS = 8;
 constexpr int CE_MAXV = 4096;
 
-__global__ void ce_count_kernel(const int64_t* __restrict__ targets, int M, int64_t ignore_index,
+// rows that count: the same predicate as ce_kernel's (an out-of-range target -- torch raises there -- is skipped by
+// both, so it can never bias the mean)
+__global__ void ce_count_kernel(const int64_t* __restrict__ targets, int M, int V, int64_t ignore_index,
                                 float* __restrict__ stats) {
   __shared__ int part[32];
   int c = 0;
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < M; i += gridDim.x * blockDim.x) c += targets[i] != ignore_index;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < M; i += gridDim.x * blockDim.x) {
+    const int64_t t = targets[i];
+    c += (t != ignore_index && t >= 0 && t < V);
+  }
   for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
   if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = c;
   __syncthreads();
@@ -124,7 +129,7 @@ extern "C" int me_cross_entropy(const void* logits, int dtype, int M, int V, int
   ME_CHECK(grad_logits == nullptr || ld_grad >= V, "me_cross_entropy: ld_grad %d < V %d", ld_grad, V);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   ME_CUDA(cudaMemsetAsync(stats, 0, 4 * sizeof(float), st));
-  ce_count_kernel<<<min((M + 255) / 256, 64), 256, 0, st>>>(targets, M, ignore_index, stats);
+  ce_count_kernel<<<min((M + 255) / 256, 64), 256, 0, st>>>(targets, M, V, ignore_index, stats);
   ME_LAUNCH_CHECK();
   if (dtype == ME_BF16) return launch_ce<bf16>(logits, M, V, ld, targets, ignore_index, grad_logits, ld_grad, stats, st);
   return launch_ce<float>(logits, M, V, ld, targets, ignore_index, grad_logits, ld_grad, stats, st);

@@ -52,13 +52,21 @@ class DataParallel:
     `model._grad_ready_hook(flat)` as soon as they are enqueued; the hook starts an asynchronous NCCL
     allreduce (AVG) of that buffer, which runs while the earlier layers' backward kernels execute.
     `sync_gradients()` waits for those reductions and reduces, in buckets, whatever gradient did not live
-    in a hooked buffer (e.g. when gradients were accumulated into pre-existing `.grad` tensors)."""
+    in a hooked buffer (e.g. when gradients were accumulated into pre-existing `.grad` tensors).
+
+    Gradient accumulation (the reference's `accumulate_step > 1`, train.py:314-319): wrap the non-boundary
+    micro-steps in `with ddp.no_sync():` -- nothing is reduced there -- and call `sync_gradients()` once before the
+    optimiser step; the accumulated `.grad` tensors are then reduced post hoc.  A backward pass that finds `.grad`
+    already populated never starts an overlapped reduction (AccumulateGrad's `p.grad += g` would race with it),
+    and first makes the compute stream wait for reductions an earlier backward pass of the same step started;
+    since averaging is linear and idempotent on already-averaged values, avg(avg(g1) + g2) = avg(g1) + avg(g2)."""
 
     def __init__(self, model: torch.nn.Module, group=None, bucket_mb: float = 256.0, overlap: bool = True):
         self.module = model
         self.group = group
         self.bucket_mb = bucket_mb
         self._pending = []
+        self.require_backward_grad_sync = True
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         if self.world > 1:
             with torch.no_grad():
@@ -70,18 +78,56 @@ class DataParallel:
     def __call__(self, *a, **kw):
         return self.module(*a, **kw)
 
+    def no_sync(self):
+        """Context manager for the non-boundary micro-steps of gradient accumulation (torch DDP's name)."""
+        ddp = self
+
+        class _NoSync:
+            def __enter__(self):
+                self.prev = ddp.require_backward_grad_sync
+                ddp.require_backward_grad_sync = False
+
+            def __exit__(self, *exc):
+                ddp.require_backward_grad_sync = self.prev
+                return False
+
+        return _NoSync()
+
+    def _accumulating(self) -> bool:
+        # the first parameter receives its gradient last (the input stage is the end of backward): a populated
+        # .grad there means an earlier backward pass of this optimiser step has already run
+        p0 = next(iter(self.module.parameters()))
+        return p0.grad is not None
+
     def _on_grads_ready(self, flat: torch.Tensor) -> None:
-        work = dist.all_reduce(flat, op=dist.ReduceOp.AVG, group=self.group, async_op=True)
-        self._pending.append((flat, work))
+        if not self.require_backward_grad_sync:
+            return
+        if self._accumulating():
+            # `.grad += g` follows on the compute stream: finish what an earlier pass started, forget it (those
+            # buffers now hold averaged + local parts and are reduced again, post hoc, by sync_gradients)
+            self._drain()
+            return
+        if dist.get_backend(self.group) == "nccl":
+            work = dist.all_reduce(flat, op=dist.ReduceOp.AVG, group=self.group, async_op=True)
+            self._pending.append((flat, work, False))
+        else:   # gloo (CPU tests) has no AVG: sum now, divide when the work is waited for
+            work = dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=self.group, async_op=True)
+            self._pending.append((flat, work, True))
+
+    def _drain(self):
+        done = set()
+        for flat, work, divide in self._pending:
+            work.wait()
+            if divide:
+                flat.div_(self.world)
+            done.add(flat.untyped_storage().data_ptr())
+        self._pending = []
+        return done
 
     def sync_gradients(self) -> None:
         if self.world == 1:
             return
-        done = set()
-        for flat, work in self._pending:
-            work.wait()
-            done.add(flat.untyped_storage().data_ptr())
-        self._pending = []
+        done = self._drain()
         rest = [p.grad for p in self.module.parameters()
                 if p.grad is not None and p.grad.untyped_storage().data_ptr() not in done]
         allreduce_mean_(rest, self.group, self.bucket_mb)

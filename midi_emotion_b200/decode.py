@@ -51,6 +51,8 @@ class KVCacheDecoder:
         self.t_dev = torch.zeros(1, device=dev, dtype=torch.int32)
         self.t_host = 0
         self.tokens_buf = torch.zeros(B, device=dev, dtype=torch.int64)
+        # static condition buffer: the captured graph holds its address, prefill() copies into it
+        self.cond_buf = torch.zeros(B, 2, **f32)
         self.cond = None
         self.Vp = (V + 7) // 8 * 8
         self.logits = torch.zeros(B, self.Vp, **tt)
@@ -66,6 +68,7 @@ class KVCacheDecoder:
         }
         self.scratch["out1_f32"], self.scratch["out1_T"] = pair()
         self.graph = None
+        self._graph_wc = None
         self._eager_steps = 0
 
     # ------------------------------------------------------------------
@@ -84,7 +87,10 @@ class KVCacheDecoder:
         if model.mode != 0:
             if condition is None:
                 raise RuntimeError("this model needs a (valence, arousal) condition")
-            self.cond = condition.to(device=self.dev, dtype=torch.float32).contiguous()
+            if tuple(condition.shape) != (self.B, 2):
+                raise RuntimeError(f"condition must be [{self.B}, 2]")
+            self.cond_buf.copy_(condition.to(device=self.dev, dtype=torch.float32))
+            self.cond = self.cond_buf
         else:
             self.cond = None
         self.reset()
@@ -112,11 +118,11 @@ class KVCacheDecoder:
         return logits[:, :model.vocab_size]
 
     # ------------------------------------------------------------------
-    def _enqueue_step(self):
+    def _enqueue_step(self, wc=None):
         model, dtype = self.model, self.dtype
         B, d, V = self.B, model.embedding_dim, model.vocab_size
         stream = _stream()
-        wc = model._weights(dtype)
+        wc = wc if wc is not None else model._weights(dtype)
         cw0, cb0, _, _ = model._cond_params()
         x_f32, x_T = self.x[0]
         _lib.call("me_embed_decode", ptr(self.tokens_buf), ptr(self.cond), ptr(model.embedding.weight), ptr(cw0),
@@ -152,18 +158,23 @@ class KVCacheDecoder:
             raise RuntimeError("call prefill() first (it stores the condition)")
         self.tokens_buf.copy_(tokens.reshape(-1), non_blocking=True)
         with torch.no_grad():
+            # the packed compute-type weight copies (re-derived here if a parameter moved); a captured graph holds
+            # their addresses, so it is dropped when they were re-allocated (.to(), load_state_dict into new storage)
+            wc = self.model._weights(self.dtype)
+            if self.graph is not None and wc is not self._graph_wc:
+                self.invalidate_graph()
             if not self.use_graph:
-                self._enqueue_step()
+                self._enqueue_step(wc)
             elif self.graph is None:
                 if self._eager_steps < 1:
-                    self._enqueue_step()          # first step eagerly: one-time kernel attribute setup
+                    self._enqueue_step(wc)        # first step eagerly: one-time kernel attribute setup
                     self._eager_steps += 1
                 else:
                     torch.cuda.synchronize()
                     g = torch.cuda.CUDAGraph()
                     with torch.cuda.graph(g):
-                        self._enqueue_step()
-                    self.graph = g
+                        self._enqueue_step(wc)
+                    self.graph, self._graph_wc = g, wc
                     g.replay()
             else:
                 self.graph.replay()
@@ -171,6 +182,7 @@ class KVCacheDecoder:
         return self.logits[:, :self.model.vocab_size]
 
     def invalidate_graph(self):
-        """Call after the model's weights changed (the graph holds pointers to packed copies)."""
+        """Drop the captured step (done automatically when the packed weight copies were re-allocated)."""
         self.graph = None
+        self._graph_wc = None
         self._eager_steps = 0

@@ -64,23 +64,49 @@ class Sampler:
 
 
 def generate(model, primer: torch.Tensor, condition: Optional[torch.Tensor], gen_len: int, sampler: Sampler,
-             max_len: Optional[int] = None, precision: str = "bf16") -> torch.Tensor:
-    """Autoregressive generation with the KV cache: returns int64 [B, primer_len + gen_len].  The model call and
-    the sampling rules are those of generate.py:99-189 (while the sequence stays inside max_input_len); no
-    device-to-host transfer happens inside the loop."""
+             max_len: Optional[int] = None, precision: str = "bf16", max_input_len: Optional[int] = None,
+             discrete_conditions: Optional[torch.Tensor] = None, varying_condition=None) -> torch.Tensor:
+    """Autoregressive generation: returns int64 [B, primer_len + gen_len].  The model call and the sampling rules are
+    those of generate.py:99-189; no device-to-host transfer happens inside the loop.
+
+    max_input_len       generate.py:101-103: the model only ever sees the last `max_input_len` tokens (the CLI default
+                        is 1216).  While the song is shorter, one KV-cache step per token; once the window slides
+                        every position moves (absolute sinusoid), cached keys are invalid, and each token costs a
+                        re-prefill of the window -- exactly the reference's full-prefix recompute, so the result
+                        stays equal to it.  Default: the model's max_seq (less the condition positions).
+    discrete_conditions int64 [B, n] emotion tokens kept in front of the window (generate.py:105-107, 78-80).
+    varying_condition   (valences [B, gen_len], arousals [B, gen_len]): interpolated conditions, generate.py:110-113;
+                        the condition feeds every position, so every step is a re-prefill.
+    max_len             cache length (default: what the window needs)."""
     from .decode import KVCacheDecoder
 
     B, t0 = primer.shape
-    max_len = max_len or min(model.max_seq, t0 + gen_len)
-    dec = KVCacheDecoder(model, B, max_len=max_len, precision=precision)
-    out = torch.empty(B, t0 + gen_len, device=primer.device, dtype=torch.int64)
+    dev = primer.device
+    n_disc = 0 if discrete_conditions is None else int(discrete_conditions.shape[1])
+    extra = 2 if model.continuous_token else 0
+    window = int(max_input_len) if max_input_len is not None else model.max_seq
+    window = min(window, model.max_seq) - extra - n_disc          # generate.py:75-80
+    if window <= 0:
+        raise ValueError("max_input_len leaves no room for tokens")
+    need = min(t0 + gen_len, window) + extra + n_disc
+    dec = KVCacheDecoder(model, B, max_len=max(need, 1) if max_len is None else max_len, precision=precision)
+    out = torch.empty(B, t0 + gen_len, device=dev, dtype=torch.int64)
     out[:, :t0] = primer
-    logits = dec.prefill(primer, condition)
+    cond = condition
     prev = primer[:, -1].contiguous()
+    logits = None
     for i in range(gen_len):
-        nxt = sampler.sample(logits, prev)
-        out[:, t0 + i] = nxt
-        if i + 1 < gen_len:
-            prev = out[:, t0 + i]
+        n = t0 + i                                   # tokens generated so far (the model input before the cut)
+        if varying_condition is not None:
+            cond = torch.stack([varying_condition[0][:, i], varying_condition[1][:, i]], dim=-1).to(dev)
+        if i == 0 or n > window or varying_condition is not None:
+            inp = out[:, max(0, n - window):n]
+            if n_disc:
+                inp = torch.cat([discrete_conditions.to(dev), inp], dim=1)
+            logits = dec.prefill(inp.contiguous(), cond)
+        else:
             logits = dec.step(prev)
+        nxt = sampler.sample(logits, prev)
+        out[:, n] = nxt
+        prev = out[:, n]
     return out

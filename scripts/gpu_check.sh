@@ -12,3 +12,6 @@ run decode tests/test_gpu_decode.py
 run fullsize tests/test_gpu_fullsize.py
 run sampling_loss tests/test_gpu_sampling.py tests/test_gpu_loss.py
 run optimizer tests/test_gpu_optimizer.py
+run regression tests/test_gpu_regression.py
+run tokens tests/test_gpu_tokens.py
+run parity_oracle tests/test_gpu_parity_oracle.py

@@ -19,7 +19,14 @@ __global__ void __launch_bounds__(NW * 32, 1) k_ld(int iters, long long* out_cyc
   __syncthreads();
   const long long t0 = clock64();
   for (int it = 0; it < iters; ++it) {
-    if (X == 64) {
+    if (X == 128) {  // two x64 loads in flight before the wait
+      uint32_t r[64], q[64];
+      tmem_ld64(base + (it & 1) * 128, r);
+      tmem_ld64(base + (it & 1) * 128 + 64, q);
+      tc_wait_ld();
+#pragma unroll
+      for (int i = 0; i < 64; i += 16) acc ^= r[i] ^ q[i];
+    } else if (X == 64) {
       uint32_t r[64];
       tmem_ld64(base + (it & 3) * 64, r);
       tc_wait_ld();
@@ -67,5 +74,8 @@ int main() {
   run<1, 32>("1 warp  x32");
   run<4, 32>("4 warps x32");
   run<8, 32>("8 warps x32");
+  run<4, 128>("4 warps 2 x x64 in flight");
+  run<8, 128>("8 warps 2 x x64 in flight");
+  run<16, 64>("16 warps x64 (4 per quarter)");
   return 0;
 }

@@ -43,6 +43,63 @@ def _worker(rank, world, port, q):
         dist.destroy_process_group()
 
 
+def _accum_worker(rank, world, port, q):
+    """The overlapped hook under gradient accumulation: backward twice per optimiser step, with and
+    without no_sync(); the result must be the average over ranks of the summed micro-step gradients."""
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        model = torch.nn.Linear(4, 3)
+        ddp = DataParallel(model)
+        model._grad_ready_hook = ddp._on_grads_ready        # what DataParallel installs on the CUDA model
+        params = list(model.parameters())
+
+        def fake_backward(scale):
+            """What the model's hand-written backward does: gradients of a group in one flat buffer, hook, then
+            autograd's AccumulateGrad (`p.grad = g` or `p.grad += g`).  The first parameter is produced last."""
+            for p in reversed(params):
+                flat = torch.full((p.numel(),), scale * (rank + 1.0))
+                model._grad_ready_hook(flat)
+                g = flat.view_as(p)
+                if p.grad is None:
+                    p.grad = g
+                else:
+                    p.grad += g
+
+        ok = True
+        mean_rank = sum(range(1, world + 1)) / world
+        for use_no_sync in (True, False):
+            for p in params:
+                p.grad = None
+            if use_no_sync:
+                with ddp.no_sync():
+                    fake_backward(1.0)
+            else:
+                fake_backward(1.0)                           # starts overlapped reductions
+            fake_backward(10.0)                              # accumulates: must not race, must not double count
+            ddp.sync_gradients()
+            ok = ok and all(torch.allclose(p.grad, torch.full_like(p, 11.0 * mean_rank)) for p in params)
+            ok = ok and not ddp._pending
+        q.put((rank, ok))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_gradient_accumulation_with_overlap_hook_world_size_2():
+    world, port = 2, _free_port()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_accum_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    results = [q.get(timeout=120) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert all(ok for _, ok in results), results
+
+
 def test_gradient_allreduce_world_size_2():
     world, port = 2, _free_port()
     ctx = mp.get_context("spawn")

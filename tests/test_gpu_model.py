@@ -14,11 +14,13 @@ if torch.cuda.is_available():
 
 # fp32: logits agree to accumulation-order noise and argmax token ids are identical (north_star).
 FP32_ATOL = 3e-5
-# bf16: north_star asks for 1e-3 relative against the reference's own bf16-autocast run.  The two
-# runs round at different points inside attention (the kernels keep S in fp32, the reference rounds
-# QK^T, Srel and their sum to bf16), so each is compared with the exact fp32 result too:
-# our error must not exceed the reference-autocast error by more than 25 %.
-BF16_VS_REF = 1.5e-2
+# bf16: north_star asks for 1e-3 relative against the reference's own bf16-autocast run.  Two bf16 runs cannot
+# agree element-wise to 1e-3 (tests/test_gpu_parity_oracle.py, module docstring and profiles/parity_r02.json:
+# 2.3e-3 for one layer, 4.4e-3 for twelve, with or without the reference's rounding sites inside attention), so
+# each run is compared with the exact fp32 result: our error must not exceed the reference-autocast error by more
+# than 10 %, and our distance to the reference's bf16 logits must not exceed the reference's own distance to fp32
+# by more than 10 % (measured at full size: 0.95-0.97 of it).
+BF16_VS_REF_RATIO = 1.10
 
 
 def _model(g, precision):
@@ -68,8 +70,8 @@ def test_forward_bf16_close_to_reference_autocast(golden):
     ref_bf16, ref_fp32 = g["logits_bf16"], g["logits_fp32"]
     ours = rel_err(logits, ref_fp32)
     theirs = rel_err(ref_bf16, ref_fp32)
-    assert ours <= 1.25 * theirs + 1e-3, (ours, theirs)
-    assert rel_err(logits, ref_bf16) < BF16_VS_REF
+    assert ours <= BF16_VS_REF_RATIO * theirs + 2e-4, (ours, theirs)
+    assert rel_err(logits, ref_bf16) <= BF16_VS_REF_RATIO * theirs + 2e-4, (rel_err(logits, ref_bf16), theirs)
     agree = (logits.argmax(-1) == ref_fp32.argmax(-1)).float().mean().item()
     ref_agree = (ref_bf16.argmax(-1) == ref_fp32.argmax(-1)).float().mean().item()
     assert agree >= ref_agree - 0.05
