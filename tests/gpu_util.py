@@ -30,3 +30,20 @@ def gemm_bf16(A, B, M, N, K, a_mn, b_mn, out_dtype, flags=0, bias=None, addend=N
               out_dtype, flags, ptr(bias), ptr(addend), ptr(mask), mask.stride(0) if mask is not None else 0,
               tile_n, splits, stream())
     return D
+
+
+def record_parity(name, values, fname="parity_small_r02.json"):
+    """Append measured parity numbers to gpurun_out/<fname> (copied to profiles/ after a GPU run)."""
+    import json
+    import os
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = os.path.join(root, "gpurun_out")
+    os.makedirs(out, exist_ok=True)
+    path = os.path.join(out, fname)
+    try:
+        data = json.load(open(path))
+    except Exception:
+        data = {}
+    data[name] = values
+    with open(path, "w") as fh:
+        json.dump(data, fh, indent=1, sort_keys=True)
