@@ -59,6 +59,11 @@ int me_device_is_sm100(void);
  * run, then collect the summed CUDA-event durations, algorithmic FLOPs (2MNK) and launch count. */
 int me_profile_enable(int capacity);
 int me_profile_collect(double* total_ms, double* total_flops, int* launches);
+/* The same per kernel class, without ending the collection: 0 = tcgen05 GEMMs, 1 = tensor-core attention forward,
+ * 2 = attention backward key side (dK, dV), 3 = attention backward query side (dQ, dE).  Algorithmic FLOPs of the
+ * attention classes: causal-minimum 2 (L^2 / 2) dh per product and head, three products each.
+ * Call before me_profile_collect(), which resets. */
+int me_profile_collect_class(int cls, double* total_ms, double* total_flops, int* launches);
 /* sizeof() of the argument structs below, for binding self-checks (ctypes/cgo/JNI mirrors). */
 int me_sizeof_attn_args(void);
 int me_sizeof_attn_bwd_args(void);
@@ -176,8 +181,16 @@ typedef struct me_attn_args {
    * q_pos0 = *pos_dev and Lk = *pos_dev + Lq are read on the device. */
   const int32_t* pos_dev;
   void* stream;
+  /* Optional, ME_ATTN_TENSOR only: the forward pass also leaves its (unnormalised, bf16) probability tiles and the
+   * per-row exponent offsets they were formed with, and the backward pass reads them back instead of recomputing
+   * QK^T, the relative band, the skew and the exponentials (the reference keeps the whole softmax output for
+   * autograd, music_multi.py:231).  Sizes: me_attention_saved_tiles().  NULL = recompute in backward. */
+  void* p_tiles;  /* T [B * H * tiles, 128, 64]: 128 query rows x 64 keys per tile, UMMA K-major swizzled rows */
+  float* m_tiles; /* f32 [B * H * tiles, 128]                                                                 */
 } me_attn_args;
 int me_attention_forward(const me_attn_args* a);
+/* tiles per (sequence, head) of p_tiles / m_tiles for a sequence length and ME_ATTN_* flags */
+int64_t me_attention_saved_tiles(int L, int flags);
 
 /* Backward of the above (full self-attention only, q_pos0 = 0, Lq = Lk).
  *   dout T same addressing as out; dq/dk/dv T with the q/k/v strides; dE f32 [max_seq, dh]
@@ -239,6 +252,9 @@ typedef struct me_layer_args {
   float* out2_f32;
   void* out2_T;
   void* stream;
+  /* optional saved attention probabilities (me_attn_args.p_tiles / m_tiles), ME_ATTN_TENSOR training only */
+  void* attn_p;
+  float* attn_m;
 } me_layer_args;
 int me_layer_forward(const me_layer_args* a);
 

@@ -31,7 +31,7 @@ class AttnArgs(C.Structure):
         ("v_sb", _i64), ("v_sh", _i64), ("v_sj", _i64),
         ("keypad", _vp), ("keypad_ld", _i64),
         ("out", _vp), ("o_sb", _i64), ("o_si", _i64),
-        ("lse", _vp), ("pos_dev", _vp), ("stream", _vp),
+        ("lse", _vp), ("pos_dev", _vp), ("stream", _vp), ("p_tiles", _vp), ("m_tiles", _vp),
     ]
 
 
@@ -41,7 +41,7 @@ class AttnBwdArgs(C.Structure):
 
 _LAYER_PTRS = ["x_f32", "x_T", "keypad", "Wqkv", "bqkv", "E", "Wo", "bo", "ln1_w", "ln1_b", "W1", "b1", "W2", "b2",
                "ln2_w", "ln2_b", "qkv", "attn_o", "lse", "proj", "z1", "mean1", "rstd1", "out1_f32", "out1_T", "h",
-               "z2", "mean2", "rstd2", "out2_f32", "out2_T", "stream"]
+               "z2", "mean2", "rstd2", "out2_f32", "out2_T", "stream", "attn_p", "attn_m"]
 
 
 class ConvertDesc(C.Structure):
@@ -101,6 +101,7 @@ _PROTOS = {
     "me_device_is_sm100": (C.c_int, []),
     "me_profile_enable": (C.c_int, [C.c_int]),
     "me_profile_collect": (C.c_int, [C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_int)]),
+    "me_profile_collect_class": (C.c_int, [C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_int)]),
     "me_debug_trace_set": (C.c_int, [_vp]),
     "me_sample_step": (C.c_int, [_vp]),
     "me_cross_entropy": (C.c_int, [_vp, C.c_int, C.c_int, C.c_int, C.c_int, _vp, C.c_int64, _vp, C.c_int, _vp, _vp]),
@@ -131,6 +132,7 @@ _PROTOS = {
     "me_attention_forward": (C.c_int, [C.POINTER(AttnArgs)]),
     "me_attention_backward": (C.c_int, [C.POINTER(AttnBwdArgs)]),
     "me_attention_backward_workspace_floats": (C.c_int64, [C.c_int] * 5),
+    "me_attention_saved_tiles": (C.c_int64, [C.c_int, C.c_int]),
     "me_layer_forward": (C.c_int, [C.POINTER(LayerArgs)]),
     "me_layer_backward": (C.c_int, [C.POINTER(LayerBwdArgs)]),
     "me_decode_layer_step": (C.c_int, [C.POINTER(DecodeLayerArgs)]),

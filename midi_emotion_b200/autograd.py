@@ -46,7 +46,7 @@ def _layer_args(model, wl: dict, lay, act: dict, x_f32, x_T, keypad, a: _Acts, l
     la.W1, la.b1, la.W2, la.b2 = ptr(wl["W1"]), ptr(lay.FFN_pre.bias), ptr(wl["W2"]), ptr(lay.FFN_suf.bias)
     la.ln2_w, la.ln2_b = ptr(lay.layernorm2.weight), ptr(lay.layernorm2.bias)
     for k in ("qkv", "attn_o", "lse", "proj", "z1", "mean1", "rstd1", "out1_f32", "out1_T", "h", "z2", "mean2",
-              "rstd2", "out2_f32", "out2_T"):
+              "rstd2", "out2_f32", "out2_T", "attn_p", "attn_m"):
         setattr(la, k, ptr(act.get(k)))
     la.stream = _stream()
     return la
@@ -103,6 +103,11 @@ def run_forward(model, tokens: torch.Tensor, cond: Optional[torch.Tensor], need_
             if need_grad:
                 act.update(z1=torch.empty(M, d, **f32), mean1=torch.empty(M, **f32), rstd1=torch.empty(M, **f32),
                            z2=torch.empty(M, d, **f32), mean2=torch.empty(M, **f32), rstd2=torch.empty(M, **f32))
+                if a.attn_impl == _lib.ATTN_TENSOR and model.save_attention_probs:
+                    # the forward kernel leaves its probability tiles for the backward kernels (the reference keeps
+                    # the softmax output for autograd too, music_multi.py:231): 128 x 64 bf16 per tile
+                    tiles = B * H * _lib.load().me_attention_saved_tiles(Ls, model._attn_flags())
+                    act.update(attn_p=torch.empty(tiles * 128 * 64, **tt), attn_m=torch.empty(tiles * 128, **f32))
             scratch = act
         else:
             act = dict(scratch)  # inference: reuse the big buffers layer after layer

@@ -23,8 +23,10 @@ NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr", "-I", INCLUDE,
 ]
+if os.environ.get("ME_EXP"):        # throw-away experiment switches for kernel tuning (-DME_EXP=<n>)
+    NVCC_FLAGS.append("-DME_EXP=" + os.environ["ME_EXP"])
 if os.environ.get("ME_TRACE") == "1":   # per-phase clock stamps in the attention backward kernel (tuning builds)
-    NVCC_FLAGS.append("-DME_ATTN_BWD_TRACE")
+    NVCC_FLAGS.append("-DME_ATTN_TRACE")
 
 
 def _nvcc() -> str:

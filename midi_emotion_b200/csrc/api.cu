@@ -143,18 +143,20 @@ extern "C" int me_sizeof_decode_layer_args(void) { return static_cast<int>(sizeo
 extern "C" int me_sizeof_sample_args(void) { return static_cast<int>(sizeof(me_sample_args)); }
 
 // ---------------------------------------------------------------------------------------------
-// Live kernel timing for bench.py: while enabled, every tcgen05 GEMM launch is bracketed by CUDA
-// events on its own stream; me_profile_collect() sums durations and algorithmic FLOPs.
+// Live kernel timing for bench.py: while enabled, every tcgen05 GEMM launch (class 0) and every tensor-core
+// attention kernel launch (class 1 forward, 2 backward key side, 3 backward query side) is bracketed by CUDA
+// events on its own stream; me_profile_collect_class() sums durations and algorithmic FLOPs per class.
 // ---------------------------------------------------------------------------------------------
 namespace me {
-struct ProfSlot { cudaEvent_t a, b; double flops; };
+struct ProfSlot { cudaEvent_t a, b; double flops; int cls; };
 static ProfSlot* g_prof = nullptr;
 static int g_prof_cap = 0, g_prof_n = 0, g_prof_on = 0;
 
-cudaEvent_t prof_begin(double flops, cudaStream_t st) {
+cudaEvent_t prof_begin(double flops, cudaStream_t st, int cls) {
   if (!g_prof_on || g_prof_n >= g_prof_cap) return nullptr;
   ProfSlot& s = g_prof[g_prof_n];
   s.flops = flops;
+  s.cls = cls;
   cudaEventRecord(s.a, st);
   return s.b;
 }
@@ -182,20 +184,28 @@ extern "C" int me_profile_enable(int capacity) {
   return 0;
 }
 
-extern "C" int me_profile_collect(double* total_ms, double* total_flops, int* launches) {
+extern "C" int me_profile_collect_class(int cls, double* total_ms, double* total_flops, int* launches) {
   using namespace me;
   double ms = 0, fl = 0;
+  int n = 0;
   for (int i = 0; i < g_prof_n; ++i) {
+    if (g_prof[i].cls != cls) continue;
     ME_CUDA(cudaEventSynchronize(g_prof[i].b));
     float t = 0.f;
     ME_CUDA(cudaEventElapsedTime(&t, g_prof[i].a, g_prof[i].b));
     ms += t;
     fl += g_prof[i].flops;
+    ++n;
   }
   if (total_ms) *total_ms = ms;
   if (total_flops) *total_flops = fl;
-  if (launches) *launches = g_prof_n;
-  g_prof_n = 0;
-  g_prof_on = 0;
+  if (launches) *launches = n;
   return 0;
+}
+
+extern "C" int me_profile_collect(double* total_ms, double* total_flops, int* launches) {
+  const int rc = me_profile_collect_class(0, total_ms, total_flops, launches);
+  me::g_prof_n = 0;
+  me::g_prof_on = 0;
+  return rc;
 }

@@ -43,6 +43,8 @@ struct FaParams {
   float* lse;
   float scale_log2;  // log2(e) / sqrt(dh)
   float sqrt_dh;
+  float* m_tiles;    // with the tmP map: the probability tiles and their exponent offsets are saved for backward
+  int tiles_per_head;
   int noncausal;     // ME_ATTN_NONCAUSAL: every key < L is visible (the band of E zero-fills itself above the diagonal)
 };
 
@@ -54,7 +56,8 @@ __device__ __forceinline__ float bf16r(float x) { return __bfloat162float(__floa
 template <int DH, bool RR>
 __global__ void __launch_bounds__(FA_THREADS, 2)
 attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
-                   const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmE, FaParams p) {
+                   const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmE,
+                   const __grid_constant__ CUtensorMap tmP, FaParams p) {
   extern __shared__ __align__(1024) uint8_t fa_smem[];
   uint8_t* sQ = fa_smem;
   uint8_t* sStage = sQ + FA_Q_BYTES;  // per stage: K | E | V  ([K ; Eband] is one 256-row B operand)
@@ -73,6 +76,9 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   const int i0 = qi * FA_BM;
   const int kmax = p.noncausal ? p.L : min(i0 + FA_BM, p.L);  // keys 0 .. kmax-1 can be visible
   const int nt = (kmax + FA_BN - 1) / FA_BN;
+  const bool save = p.m_tiles != nullptr;
+  const int64_t tile0 = (static_cast<int64_t>(b) * p.H + h) * p.tiles_per_head +
+                        (p.noncausal ? static_cast<int64_t>(qi) * ((p.L + FA_BN - 1) / FA_BN) : static_cast<int64_t>(qi) * (qi + 1));
 
   // Thread 0 is also the TMA producer and the MMA issuer: the per-tile schedule is a strict sequence
   // (S/R MMAs -> softmax -> P.V MMA -> accumulate), the overlap comes from the second CTA on the SM.
@@ -231,6 +237,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     }
     l = l * alpha + rs;
     m = m_new;
+    if (save) p.m_tiles[(tile0 + t) * FA_BM + a] = m_use;   // P[a, :] of this tile = exp2(x c - m_use)
     fence_proxy_async_smem();  // generic-proxy writes of P -> visible to the tensor core (async proxy)
     tc_fence_before();
     __syncthreads();           // P complete, S/R consumed by every row
@@ -243,6 +250,10 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
                     make_smem_desc_sw128(v_addr + k * 2048, 8192, 1024), idesc_o, k > 0);
         umma_commit(o_full);
         umma_commit(&kv_free[s]);
+        if (save) {   // the tile of P, as the tensor core reads it, goes to the saved-activation tensor
+          tma_store_2d(&tmP, sP, 0, static_cast<int>((tile0 + t) * FA_BM));
+          bulk_commit();
+        }
       }
       __syncwarp();
     }
@@ -260,6 +271,10 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     if (warp == 0 && t + 2 < nt) {
       mbar_wait(&kv_free[s], ph);
       if (elect_one()) load_tile(t + 2);
+      __syncwarp();
+    }
+    if (warp == 0 && save) {   // (elect.sync names the same lane every time: the one that committed the store)
+      if (elect_one()) bulk_wait_read_all();
       __syncwarp();
     }
     __syncthreads();           // P.V tile read out of TMEM by every row before the next S/R MMAs
@@ -291,7 +306,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
 
 template <int DH, bool RR>
 static int launch_fwd(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const CUtensorMap& te,
-                      const FaParams& p, dim3 grid, cudaStream_t st) {
+                      const CUtensorMap& tp, const FaParams& p, dim3 grid, cudaStream_t st) {
   auto kern = attn_fwd_tc_kernel<DH, RR>;
   static bool configured = false;
   if (!configured) {
@@ -299,7 +314,9 @@ static int launch_fwd(const CUtensorMap& tq, const CUtensorMap& tk, const CUtens
     ME_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
     configured = true;
   }
-  kern<<<grid, FA_THREADS, FA_SMEM, st>>>(tq, tk, tv, te, p);
+  cudaEvent_t pe = prof_begin(3.0 * attn_unit_flops(p.B, p.H, p.L, DH), st, 1);   // QK^T, QE^T, PV
+  kern<<<grid, FA_THREADS, FA_SMEM, st>>>(tq, tk, tv, te, tp, p);
+  prof_end(pe, st);
   ME_LAUNCH_CHECK();
   return 0;
 }
@@ -332,16 +349,33 @@ int launch_attn_fwd_tc(const me_attn_args* a) {
   p.sqrt_dh = sqrtf(static_cast<float>(a->dh));
   p.scale_log2 = 1.4426950408889634f / p.sqrt_dh;
   p.noncausal = (a->flags & ME_ATTN_NONCAUSAL) ? 1 : 0;
+  p.m_tiles = nullptr;
+  p.tiles_per_head = static_cast<int>(me_attention_saved_tiles(a->Lq, a->flags));
+  CUtensorMap tp = te;   // (unused unless the tiles are saved)
+  if (a->p_tiles != nullptr && a->m_tiles != nullptr) {
+    const uint64_t rows = static_cast<uint64_t>(a->B) * a->H * p.tiles_per_head * FA_BM;
+    ME_CHECK(rows < (1ull << 31), "me_attention_forward: saved-tile tensor too large");
+    const uint64_t dims[2] = {64, rows};
+    const uint64_t strides[1] = {64};
+    const uint32_t box[2] = {64, FA_BM};
+    if (make_tmap_nd_bf16(&tp, a->p_tiles, 2, dims, strides, box)) return 1;
+    p.m_tiles = a->m_tiles;
+  }
   dim3 grid((a->Lq + FA_BM - 1) / FA_BM, a->H, a->B);
   cudaStream_t st = static_cast<cudaStream_t>(a->stream);
   if (a->flags & ME_ATTN_REF_ROUNDING) {
-    if (a->dh == 64) return launch_fwd<64, true>(tq, tk, tv, te, p, grid, st);
-    if (a->dh == 48) return launch_fwd<48, true>(tq, tk, tv, te, p, grid, st);
-    return launch_fwd<32, true>(tq, tk, tv, te, p, grid, st);
+    if (a->dh == 64) return launch_fwd<64, true>(tq, tk, tv, te, tp, p, grid, st);
+    if (a->dh == 48) return launch_fwd<48, true>(tq, tk, tv, te, tp, p, grid, st);
+    return launch_fwd<32, true>(tq, tk, tv, te, tp, p, grid, st);
   }
-  if (a->dh == 64) return launch_fwd<64, false>(tq, tk, tv, te, p, grid, st);
-  if (a->dh == 48) return launch_fwd<48, false>(tq, tk, tv, te, p, grid, st);
-  return launch_fwd<32, false>(tq, tk, tv, te, p, grid, st);
+  if (a->dh == 64) return launch_fwd<64, false>(tq, tk, tv, te, tp, p, grid, st);
+  if (a->dh == 48) return launch_fwd<48, false>(tq, tk, tv, te, tp, p, grid, st);
+  return launch_fwd<32, false>(tq, tk, tv, te, tp, p, grid, st);
 }
 
 }  // namespace me
+
+extern "C" int64_t me_attention_saved_tiles(int L, int flags) {
+  const int64_t nq = (L + me::FA_BM - 1) / me::FA_BM, nkt = (L + me::FA_BN - 1) / me::FA_BN;
+  return (flags & ME_ATTN_NONCAUSAL) ? nq * nkt : nq * (nq + 1);
+}

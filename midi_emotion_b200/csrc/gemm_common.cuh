@@ -5,7 +5,7 @@
 
 namespace me {
 
-cudaEvent_t prof_begin(double flops, cudaStream_t st);
+cudaEvent_t prof_begin(double flops, cudaStream_t st, int cls = 0);   // (declared again in attention_tc.cuh)
 void prof_end(cudaEvent_t e, cudaStream_t st);
 
 struct GemmParams {

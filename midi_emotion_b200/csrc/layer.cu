@@ -78,6 +78,8 @@ static void fill_attn(const me_layer_args* a, me_attn_args* t) {
   t->lse = a->lse;
   t->pos_dev = nullptr;
   t->stream = a->stream;
+  t->p_tiles = a->attn_p;
+  t->m_tiles = a->attn_m;
 }
 
 // attention output -> out-projection -> LN1 -> FFN -> LN2 (shared by forward and the decode step)

@@ -100,6 +100,9 @@ class MusicTransformer(nn.Module):
         # True: the tensor-core attention rounds QK^T, Srel, their sum and the scaled logits to bf16 exactly where
         # the reference does under autocast (music_multi.py:215-222); default keeps them in fp32
         self.reference_rounding = False
+        # training, tensor-core attention: keep the probability tiles of the forward pass for the backward kernels
+        # (0.44 GB per layer at 12 heads x 32 sequences x 1024 tokens) instead of recomputing them
+        self.save_attention_probs = True
 
         self.embedding = nn.Embedding(vocab_size, embedding_dim - d_condition, padding_idx=pad_token)
         if self.continuous_token:

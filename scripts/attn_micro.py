@@ -34,6 +34,11 @@ a.q_si = a.k_sj = a.v_sj = 3 * d
 a.keypad, a.keypad_ld = None, L
 a.out, a.o_sb, a.o_si = out.data_ptr(), L * d, d
 a.lse, a.pos_dev, a.stream = lse.data_ptr(), None, st
+if os.environ.get("SAVED", "1") == "1":
+    tiles = B * H * _lib.load().me_attention_saved_tiles(L, 0)
+    p_tiles = torch.empty(tiles * 128 * 64, device="cuda", dtype=torch.bfloat16)
+    m_tiles = torch.empty(tiles * 128, device="cuda")
+    a.p_tiles, a.m_tiles = p_tiles.data_ptr(), m_tiles.data_ptr()
 ba = _lib.AttnBwdArgs()
 ba.f = a
 ba.dout = dout.data_ptr()
@@ -61,18 +66,20 @@ print(f"attention B={B} H={H} L={L} dh={dh}: fwd {t_f * 1e3:.1f} us ({fwd_flops 
       f"bwd {t_b * 1e3:.1f} us ({2.5 * fwd_flops / t_b / 1e9:.1f} TFLOP/s useful, incl. prep/convert)")
 
 if os.environ.get("TRACE"):
-    # per-phase clock stamps of one CTA of the backward kernel (me_debug_trace_set)
-    buf = torch.zeros(3 * 16 * 16, dtype=torch.int64, device="cuda")
+    # clock stamps of one CTA of the query-side backward kernel (ME_TRACE=1 build, me_debug_trace_set)
+    buf = torch.zeros(2 * 3 * 20 * 8, dtype=torch.int64, device="cuda")
     _lib.call("me_debug_trace_set", buf.data_ptr())
     _lib.call("me_attention_backward", C.byref(ba))
     torch.cuda.synchronize()
     _lib.call("me_debug_trace_set", None)
-    t = buf.cpu().view(3, 16, 16)
-    t0 = int(t[t > 0].min())
-    names = {0: "warp0", 1: "warp7", 2: "ctrl"}
-    for role in range(3):
-        for st in range(16):
-            row = t[role, st]
-            if int(row.max()) == 0:
-                continue
-            print(names[role], "step", st, " ".join(f"{(int(v) - t0) if v > 0 else -1:7d}" for v in row[:15]))
+    for kern, t in zip(("key-side", "query-side"), buf.cpu().view(2, 3, 20, 8)):
+        if int(t.max()) == 0:
+            continue
+        t0 = int(t[t > 0].min())
+        names = {0: "thread", 1: "mma   ", 2: "loader"}
+        for role in range(3):
+            for st in range(20):
+                row = t[role, st]
+                if int(row.max()) == 0:
+                    continue
+                print(kern, names[role], "step", st, " ".join(f"{(int(v) - t0) if v > 0 else -1:7d}" for v in row[:6]))

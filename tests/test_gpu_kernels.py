@@ -319,7 +319,7 @@ def test_embed_forward_matches_oracle(golden):
     assert torch.equal(keypad.cpu().bool(), mask[:, -1, :])
 
 
-def _run_attention_forward(impl, qkv, E, keypad, B, H, L, dh):
+def _run_attention_forward(impl, qkv, E, keypad, B, H, L, dh, save_probs=False):
     MS = E.shape[0]
     d = H * dh
     out = torch.full((B, L, d), float("nan"), device="cuda", dtype=qkv.dtype)
@@ -336,6 +336,10 @@ def _run_attention_forward(impl, qkv, E, keypad, B, H, L, dh):
     a.keypad, a.keypad_ld = (keypad.data_ptr() if keypad is not None else None), L
     a.out, a.o_sb, a.o_si = out.data_ptr(), L * d, d
     a.lse, a.pos_dev, a.stream = lse.data_ptr(), None, stream()
+    if save_probs:      # the forward pass leaves its probability tiles for backward
+        tiles = B * H * _lib.load().me_attention_saved_tiles(L, 0)
+        a._keep = (torch.empty(tiles * 128 * 64, device="cuda", dtype=torch.bfloat16), torch.empty(tiles * 128, device="cuda"))
+        a.p_tiles, a.m_tiles = a._keep[0].data_ptr(), a._keep[1].data_ptr()
     _lib.call("me_attention_forward", C.byref(a))
     return out, lse, a
 
@@ -391,7 +395,8 @@ def _run_attention_backward(impl, a, qkv, out, lse, dout, B, H, L, dh):
 @pytest.mark.parametrize("B,H,L,dh", [(2, 2, 37, 48), (1, 3, 130, 64), (2, 1, 64, 32), (2, 2, 300, 64),
                                       (1, 2, 1024, 64), (1, 1, 2048, 64), (2, 4, 1026, 48)])
 @pytest.mark.parametrize("pad", [False, True])
-def test_attention_tensor_core_backward(B, H, L, dh, pad):
+@pytest.mark.parametrize("saved", [False, True], ids=["recompute", "saved_probs"])
+def test_attention_tensor_core_backward(B, H, L, dh, pad, saved):
     MS = 2048
     d = H * dh
     g = torch.Generator(device="cuda").manual_seed(L * 3 + dh)
@@ -402,7 +407,7 @@ def test_attention_tensor_core_backward(B, H, L, dh, pad):
         keypad[0, L - min(L // 3, 70):] = 1
         keypad[B - 1, 1::5] = 1
     kp = keypad if pad else None
-    out, lse, a = _run_attention_forward(_lib.ATTN_TENSOR, qkv, E, kp, B, H, L, dh)
+    out, lse, a = _run_attention_forward(_lib.ATTN_TENSOR, qkv, E, kp, B, H, L, dh, save_probs=saved)
     dout = torch.randn(B, L, d, device="cuda", generator=g).to(torch.bfloat16)
     g_tc, dE_tc = _run_attention_backward(_lib.ATTN_TENSOR, a, qkv, out, lse, dout, B, H, L, dh)
     torch.cuda.synchronize()
