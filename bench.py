@@ -146,23 +146,68 @@ def synthetic_batch(cfg, B, L, seed, device=None, pin=False):
 # ----------------------------------------------------------------------------------------------
 # reference arm: the reference algorithm (oracle port) on the host cores
 # ----------------------------------------------------------------------------------------------
+def _reference_model(cfg):
+    """The UNMODIFIED reference model package when /root/reference is on this machine (the build container), else
+    None (the GPU box): the arm then times the oracle port of the same arithmetic."""
+    src = "/root/reference/src"
+    if not os.path.isdir(os.path.join(src, "models")):
+        return None
+    try:
+        sys.path.insert(0, src)
+        from models.build_model import build_model as ref_build   # noqa: E402
+        torch.manual_seed(1234)
+        model, _ = ref_build(dict(cfg, dropout=0.0))
+        return model.train()
+    except Exception:
+        return None
+    finally:
+        if src in sys.path:
+            sys.path.remove(src)
+
+
 def cpu_train_tokens_per_s(steps, warmup, B=1, L=SEQ_LEN, threads=None, cfg=None):
+    """The reference's training step on the host cores: forward, CE (ignore_index = pad), backward,
+    clip_grad_norm_(1.0), torch.optim.Adam(lr 2e-5) -- train.py:276-292,307-325.  Returns (tokens/s, ms/step,
+    threads, kind): kind "reference" = the reference's own nn.Module, "port" = the oracle restatement of its forward
+    (both under torch autograd + torch.optim.Adam)."""
     from oracle import midi_oracle as O
     threads = threads or os.cpu_count() or 1
     torch.set_num_threads(threads)
     cfg = dict(cfg or CFG2, dropout=0.0)
-    params = O.init_params(cfg, seed=1234, e_scale=0.2)
     tokens, cond, target = synthetic_batch(cfg, B, L, 1002)
-    state = {}
+    ref = _reference_model(cfg)
+    if ref is not None:
+        kind = "reference"
+        params = list(ref.parameters())
+        with torch.no_grad():
+            for n, p in ref.named_parameters():
+                if n.endswith("rga.E"):
+                    p.mul_(0.2)
+
+        def loss_of():
+            out = ref(tokens, cond)
+            return torch.nn.functional.cross_entropy(out.reshape(-1, out.size(-1)), target.reshape(-1), ignore_index=0)
+    else:
+        kind = "port"
+        leaves = {k: v.clone().requires_grad_(True) for k, v in O.init_params(cfg, seed=1234, e_scale=0.2).items()}
+        params = list(leaves.values())
+
+        def loss_of():
+            return O.loss_fn(O.forward(leaves, cfg, tokens, cond), target)
+    opt = torch.optim.Adam(params, lr=2e-5)
     times = []
     for i in range(warmup + steps):
         t0 = time.perf_counter()
-        _, params = O.train_step(params, state, cfg, tokens, cond, target, lr=2e-5, clip=1.0)
+        loss = loss_of()
+        loss.backward()
+        torch.nn.utils.clip_grad_norm_(params, 1.0)
+        opt.step()
+        opt.zero_grad(set_to_none=True)
         dt = time.perf_counter() - t0
         if i >= warmup:
             times.append(dt)
     total = sum(times)
-    return B * target.size(1) * len(times) / total, 1e3 * total / len(times), threads
+    return B * target.size(1) * len(times) / total, 1e3 * total / len(times), threads, kind
 
 
 def run_reference(args, rank):
@@ -171,15 +216,17 @@ def run_reference(args, rank):
     steps, warmup = max(1, args.steps), max(0, args.warmup)
     cfg, L, Ls, _, metric, label = workload(args.workload)
     # bounded sample: B=1 sequence of the same model/seq_len per step (the full batch of 32 is ~2 min/step)
-    tps, ms, threads = cpu_train_tokens_per_s(steps, warmup, B=1, L=L, cfg=cfg)
-    sample = f"{steps} steps of batch 1 x seq {Ls} (same model, fp32, fwd+CE+bwd+clip+Adam), {threads} threads"
+    tps, ms, threads, kind = cpu_train_tokens_per_s(steps, warmup, B=1, L=L, cfg=cfg)
+    sample = f"{steps} steps of batch 1 x seq {Ls} (same model, fp32, fwd+CE+bwd+clip_grad_norm_+torch.optim.Adam), {threads} threads"
     line = {
         "impl": "reference", "metric": metric, "value": tps, "unit": "tokens/s", "n_gpus": args.gpus, "steps": steps,
         "warmup": warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
         "config": {"workload": "train step (fwd+CE+bwd+clip+Adam) " + label,
-                   "global_batch": 1, "seq_len": Ls, "note": "oracle port of the reference PyTorch path on CPU"},
-        "cpu_baseline": {"value": tps, "unit": "tokens/s", "cores": threads, "kind": "port", "sample": sample},
+                   "global_batch": 1, "seq_len": Ls,
+                   "note": ("the unmodified reference model package on CPU" if kind == "reference" else
+                            "oracle port of the reference PyTorch path on CPU (/root/reference is not on this machine)")},
+        "cpu_baseline": {"value": tps, "unit": "tokens/s", "cores": threads, "kind": kind, "sample": sample},
         "e2e": {"value": tps, "unit": "tokens/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -210,100 +257,93 @@ def cpu_decode_tokens_per_s(prefix=1024, B=4, steps=2, threads=None):
 
 
 # ----------------------------------------------------------------------------------------------
-# decode leg (BASELINE configs[3]): KV-cache step at B=256, T=2048, measured mid-sequence
+# decode leg (BASELINE configs[3]): a real generation -- prefill + one KV-cache step per token to 2048
 # ----------------------------------------------------------------------------------------------
-def decode_leg(model, peaks, B=256, T=2048, t_mid=1024, steps=20):
-    """Step latency is linear in the prefix length, so the mid-sequence step is the average step of a
-    full 2048-token generation.  HBM-algorithmic bytes: weights once + K/V rows of every sequence."""
+def decode_leg(model, peaks, B=256, T=2048, t0=2):
+    """generate.py:99-189 for 64 primers x 4 (valence, arousal) pairs = 256 sequences: prefill of the primer, then
+    T - t0 KV-cache steps, each followed by the on-device sampling step (special symbols excluded, temperatures
+    1.2 / 1.2, repeat penalty 0.5, top-p 0.7); nothing touches the host inside the loop.  `value`: generated
+    tokens/s over the whole generation, device-timed; `e2e`: the same with the primer coming from pinned host memory
+    and the generated tokens copied back inside the timed region.  HBM-algorithmic bytes: per step the weights once
+    plus the K / V rows of every sequence up to the current position."""
     from midi_emotion_b200 import KVCacheDecoder, Sampler
     model.eval()
-    opt_free = torch.cuda.empty_cache
-    opt_free()
-    dec = KVCacheDecoder(model, B, max_len=T, precision="bf16")
+    torch.cuda.empty_cache()
     dev = next(model.parameters()).device
-    g = torch.Generator(device=dev).manual_seed(5)
-    cond = torch.rand(B, 2, device=dev, generator=g) * 2 - 1
-    tok = torch.randint(1, CFG2["vocab_size"], (B, 2), device=dev, generator=g)
-    dec.prefill(tok, cond)
-    for c in dec.k_cache + dec.v_cache:
-        c.normal_(0, 0.5, generator=g)
-    nxt = torch.randint(1, CFG2["vocab_size"], (B,), device=dev, generator=g)
-    for _ in range(3):
-        dec.step(nxt)                       # eager step, graph capture, first replay
-    dec.t_dev.fill_(t_mid)
-    dec.t_host = t_mid
-    torch.cuda.synchronize()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    # the generation loop of generate.py:99-189 with every rule of its sampling step (special symbols excluded,
-    # temperatures 1.2/1.2, repeat penalty 0.5, top-p 0.7) on the device: model step -> me_sample_step -> next step
-    exclude = torch.zeros(CFG2["vocab_size"], dtype=torch.uint8)
+    V = CFG2["vocab_size"]
+    g = torch.Generator().manual_seed(5)
+    primers = torch.randint(5, V, (B // 4, t0), generator=g)
+    primers[:, 0] = 1                                                    # <START>
+    primer_host = primers.repeat_interleave(4, dim=0).contiguous().pin_memory()
+    va = torch.tensor([[0.8, 0.8], [0.8, -0.8], [-0.8, 0.8], [-0.8, -0.8]])   # train.py:361-366
+    cond_host = va.repeat(B // 4, 1).contiguous().pin_memory()
+    exclude = torch.zeros(V, dtype=torch.uint8)
     exclude[:5] = 1
-    sampler = Sampler(B, CFG2["vocab_size"], exclude=exclude, seed=9)
-    nxt = sampler.sample(dec.step(nxt), nxt)
+    dec = KVCacheDecoder(model, B, max_len=T, precision="bf16")
+    out = torch.empty(B, T, device=dev, dtype=torch.int64)
+    out_host = torch.empty(B, T, dtype=torch.int64).pin_memory()
+
+    def generate_once(seed):
+        sampler = Sampler(B, V, exclude=exclude, seed=seed)
+        primer = primer_host.to(dev, non_blocking=True)
+        cond = cond_host.to(dev, non_blocking=True)
+        out[:, :t0] = primer
+        logits = dec.prefill(primer, cond)
+        prev = primer[:, -1].contiguous()
+        for t in range(t0, T):
+            nxt = sampler.sample(logits, prev)
+            out[:, t] = nxt
+            prev = out[:, t]
+            if t + 1 < T:
+                logits = dec.step(prev)
+
+    # warm-up: a short generation (kernel attribute setup, CUDA-graph capture of the step)
+    dec_T = T
+    T = 16
+    generate_once(1)
+    T = dec_T
     torch.cuda.synchronize()
+    e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
     e0.record()
-    for _ in range(steps):
-        logits = dec.step(nxt)
-        nxt = sampler.sample(logits, nxt)   # device side, no host synchronisation inside the loop
+    generate_once(9)
     e1.record()
+    out_host.copy_(out, non_blocking=True)
+    e2.record()
     torch.cuda.synchronize()
-    ms = e0.elapsed_time(e1) / steps
-    d, NL, V = CFG2["d_model"], CFG2["n_layer"], CFG2["vocab_size"]
-    kv = B * NL * 2 * (t_mid + steps / 2) * d * 2
+    ms_dev, ms_e2e = e0.elapsed_time(e1), e0.elapsed_time(e2)
+    gen = B * (T - t0)
+    d, NL = CFG2["d_model"], CFG2["n_layer"]
     w = NL * 12 * d * d * 2 + d * V * 2
-    gbs = (kv + w) / ms / 1e6
+    bytes_total = sum(w + B * NL * 2 * t * d * 2 for t in range(t0, T - 1))    # step at position t reads keys 0..t
+    gbs = bytes_total / ms_dev / 1e6
+    distinct = int(torch.unique(out_host[:, t0:]).numel())
     model.train()
-    return {"metric": "decode tokens/sec @ seq2048 (KV cache + on-device sampling, B=256, mid-sequence step t=1024)",
-            "value": B / ms * 1e3, "unit": "tokens/s", "ms_per_step": ms, "batch": B, "max_len": T,
+    return {"metric": "decode tokens/sec @ seq2048 (prefill + 2046 KV-cache steps with on-device sampling, B=256)",
+            "value": gen / ms_dev * 1e3, "unit": "tokens/s", "ms_total": ms_dev, "ms_per_step": ms_dev / (T - t0),
+            "batch": B, "max_len": T, "primer_len": t0, "distinct_tokens_generated": distinct,
+            "e2e": {"value": gen / ms_e2e * 1e3, "unit": "tokens/s", "h2d_bytes": primer_host.numel() * 8 + cond_host.numel() * 4,
+                    "d2h_bytes": out_host.numel() * 8},
             "roofline": {"bound": "hbm", "achieved": gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                         "frac": gbs / peaks["hbm_gbs"], "algorithmic_bytes_per_step": kv + w}}
+                         "frac": gbs / peaks["hbm_gbs"], "algorithmic_bytes_total": bytes_total}}
 
 
 # ----------------------------------------------------------------------------------------------
 # this repo's arm
 # ----------------------------------------------------------------------------------------------
-def main():
-    ap = argparse.ArgumentParser()
-    ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
-    ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="cfg2",
-                    choices=["cfg2", "cfg3", "discrete_token", "continuous_token", "continuous_concat", "none"],
-                    help="cfg2 = BASELINE configs[1] (the quoted metric); cfg3 = configs[2]; a conditioning mode = "
-                         "that row of the configs[4] sweep")
-    ap.add_argument("--batch", type=int, default=None, help="sequences per GPU (default: the workload's)")
-    ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--attn", default="auto", choices=["auto", "simt", "tensor"])
-    ap.add_argument("--no-decode", action="store_true", help="skip the KV-cache decode measurement (configs[3])")
-    ap.add_argument("--torch-loss", action="store_true", help="PyTorch cross-entropy instead of the fused kernel")
-    ap.add_argument("--optim", default=DEFAULT_OPTIM, choices=["torch", "fused"],
-                    help="torch: clip_grad_norm_ + torch.optim.Adam(fused=True); fused: ClipAdam (csrc/optimizer.cu)")
-    args = ap.parse_args()
-    rank = int(os.environ.get("RANK", "0"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    if args.impl == "reference":
-        run_reference(args, rank)
-        return
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py: no CUDA device (the B200 path has no CPU fallback)")
+KERNEL_CLASSES = {
+    0: "gemm_tc_kernel / gemm_tc2_kernel (tcgen05 bf16 GEMMs: every Linear, dgrad and wgrad)",
+    1: "attn_fwd_tc_kernel (relative attention forward)",
+    2: "attn_bwd_tc_kernel (relative attention backward, key side: dK, dV)",
+    3: "attn_bwd_q_tc_kernel (relative attention backward, query side: dQ, dE)",
+}
 
+
+def train_leg(args, CFG, L, Ls, B, K, W, dev, rank, world, lib, with_e2e=True, check_ddp=False):
+    """Build the model, run W warm-up and K timed steps (inputs resident), then K steps end to end from pinned host
+    buffers.  Returns a dict of raw measurements (rank-local times are reduced with MAX over ranks)."""
     import torch.distributed as dist
     from midi_emotion_b200 import ClipAdam, _lib, build_model, cross_entropy
     from midi_emotion_b200.ddp import DataParallel
-
-    torch.cuda.set_device(local_rank)
-    dev = torch.device("cuda", local_rank)
-    if world > 1:
-        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", device_id=dev)
-    lib = _lib.load()
-    W, K = max(3, args.warmup), max(1, args.steps)
-    if args.workload == "continuous_concat":
-        args.workload = "cfg2"
-    CFG, L, Ls, B, metric, label = workload(args.workload)
-    B = args.batch or B
 
     torch.manual_seed(1234)
     model, _ = build_model(dict(CFG))
@@ -323,7 +363,7 @@ def main():
     host = [synthetic_batch(CFG, B, L, 1002 + 17 * rank + i, pin=True) for i in range(2)]
     resident = [tuple(t.to(dev) for t in h) for h in host]
 
-    def train_step(tokens, cond, target):
+    def forward_backward(tokens, cond, target):
         with torch.autocast("cuda", dtype=torch.bfloat16):
             logits = model(tokens, cond)
         if args.torch_loss:   # the reference's nn.CrossEntropyLoss (train.py:124,288-290) on the logits
@@ -332,6 +372,10 @@ def main():
         else:                 # the same loss, fused with its gradient and the top-k counts (me_cross_entropy)
             loss = cross_entropy(logits, target, ignore_index=0)
         loss.backward()
+        return loss
+
+    def train_step(tokens, cond, target):
+        loss = forward_backward(tokens, cond, target)
         ddp.sync_gradients()
         if args.optim == "torch":
             torch.nn.utils.clip_grad_norm_(model.parameters(), 1.0)
@@ -344,58 +388,153 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    ddp_check = None
+    if check_ddp and world > 1:
+        # one-off: the overlapped, bucketed allreduce must leave on every rank the mean over ranks of the local
+        # gradients.  Reference: a hook-less backward, then ONE plain allreduce of the concatenated gradients.
+        p_drop = model.dropout_p
+        model.dropout_p = 0.0
+        hook = model._grad_ready_hook
+        model._grad_ready_hook = None
+        forward_backward(*resident[0])
+        flat = torch.cat([p.grad.reshape(-1) for p in model.parameters()])
+        dist.all_reduce(flat)
+        flat /= world
+        opt.zero_grad(set_to_none=True)
+        model._grad_ready_hook = hook
+        forward_backward(*resident[0])
+        ddp.sync_gradients()
+        got = torch.cat([p.grad.reshape(-1) for p in model.parameters()])
+        err = float((got - flat).norm() / flat.norm().clamp_min(1e-30))
+        same = torch.tensor([float(got.double().sum())], device=dev, dtype=torch.float64)
+        gathered = [torch.zeros_like(same) for _ in range(world)]
+        dist.all_gather(gathered, same)
+        ddp_check = {"rel_l2_err_vs_plain_allreduce_mean": err, "ranks_hold_identical_gradients":
+                     bool(all(float(x) == float(gathered[0]) for x in gathered)), "world": world,
+                     "tolerance": 2e-2, "ok": bool(err < 2e-2),
+                     "note": "bf16 split-K / atomic accumulation order differs between the two backward passes"}
+        opt.zero_grad(set_to_none=True)
+        model.dropout_p = p_drop
+
     for i in range(W):
         train_step(*resident[i % 2])
     barrier()
 
     # ---- timed region 1: inputs resident in HBM
-    sampler = ClockSampler(local_rank)
+    sampler = ClockSampler(dev.index)
     sampler.start()
-    n_gemm_slots = 64 * CFG["n_layer"] * K + 64
-    lib.me_profile_enable(n_gemm_slots)
+    lib.me_profile_enable((64 + 8) * CFG["n_layer"] * K + 64)
     launches0 = _lib.launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     e0.record()
+    h0 = time.perf_counter()
     for i in range(K):
         loss = train_step(*resident[i % 2])
+    host_ms = 1e3 * (time.perf_counter() - h0)     # time the host needed to ENQUEUE the K steps (no sync inside)
     e1.record()
     barrier()
     ms = e0.elapsed_time(e1)
     launches = _lib.launch_count() - launches0
-    g_ms, g_fl, g_n = ctypes.c_double(), ctypes.c_double(), ctypes.c_int()
-    lib.me_profile_collect(ctypes.byref(g_ms), ctypes.byref(g_fl), ctypes.byref(g_n))
+    classes = {}
+    for cls in sorted(KERNEL_CLASSES, reverse=True):    # class 0 last: me_profile_collect ends the collection
+        c_ms, c_fl, c_n = ctypes.c_double(), ctypes.c_double(), ctypes.c_int()
+        if cls == 0:
+            lib.me_profile_collect(ctypes.byref(c_ms), ctypes.byref(c_fl), ctypes.byref(c_n))
+        else:
+            lib.me_profile_collect_class(cls, ctypes.byref(c_ms), ctypes.byref(c_fl), ctypes.byref(c_n))
+        classes[cls] = (c_ms.value, c_fl.value, c_n.value)
     clocks = sampler.stop()
     final_loss = float(loss.item())
 
     # ---- timed region 2: end to end from pinned host buffers, loss read back every step
-    barrier()
-    e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e2.record()
-    for i in range(K):
-        tok, cond, tgt = (t.to(dev, non_blocking=True) for t in host[i % 2])
-        lv = train_step(tok, cond, tgt).item()
-    e3.record()
-    barrier()
-    ms_e2e = e2.elapsed_time(e3)
+    ms_e2e = None
+    if with_e2e:
+        barrier()
+        e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e2.record()
+        for i in range(K):
+            tok, cond, tgt = (t.to(dev, non_blocking=True) for t in host[i % 2])
+            train_step(tok, cond, tgt).item()
+        e3.record()
+        barrier()
+        ms_e2e = e2.elapsed_time(e3)
 
     if world > 1:
-        t = torch.tensor([ms, ms_e2e], device=dev)
+        t = torch.tensor([ms, ms_e2e or 0.0], device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms, ms_e2e = float(t[0]), float(t[1])
+        ms, ms_e2e = float(t[0]), (float(t[1]) if with_e2e else None)
+    h2d = sum(t.numel() * t.element_size() for t in host[0])
+    return dict(model=model, ms=ms, ms_e2e=ms_e2e, host_ms=host_ms, launches=launches, classes=classes, clocks=clocks,
+                final_loss=final_loss, h2d=h2d, ddp_check=ddp_check, opt=opt)
 
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="cfg2",
+                    choices=["cfg2", "cfg3", "discrete_token", "continuous_token", "continuous_concat", "none"],
+                    help="cfg2 = BASELINE configs[1] (the quoted metric); cfg3 = configs[2]; a conditioning mode = "
+                         "that row of the configs[4] sweep")
+    ap.add_argument("--batch", type=int, default=None, help="sequences per GPU (default: the workload's)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--attn", default="auto", choices=["auto", "simt", "tensor"])
+    ap.add_argument("--no-decode", action="store_true", help="skip the KV-cache decode measurement (configs[3])")
+    ap.add_argument("--no-cfg3-leg", action="store_true", help="skip the short configs[2] leg (24L/1024d, seq 2048)")
+    ap.add_argument("--torch-loss", action="store_true", help="PyTorch cross-entropy instead of the fused kernel")
+    ap.add_argument("--optim", default=DEFAULT_OPTIM, choices=["torch", "fused"],
+                    help="torch: clip_grad_norm_ + torch.optim.Adam(fused=True); fused: ClipAdam (csrc/optimizer.cu)")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (the B200 path has no CPU fallback)")
+
+    import torch.distributed as dist
+    from midi_emotion_b200 import _lib
+
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    lib = _lib.load()
+    W, K = max(3, args.warmup), max(1, args.steps)
+    if args.workload == "continuous_concat":
+        args.workload = "cfg2"
+    CFG, L, Ls, B, metric, label = workload(args.workload)
+    B = args.batch or B
+
+    r = train_leg(args, CFG, L, Ls, B, K, W, dev, rank, world, lib, with_e2e=True, check_ddp=True)
+    model, ms, ms_e2e = r["model"], r["ms"], r["ms_e2e"]
+
+    line = None
     if rank == 0:
         peaks = load_peaks()
         tokens_per_step = world * B * Ls     # positions through the stack (continuous_token: two of them are the condition)
         value = tokens_per_step * K / (ms / 1e3)
         e2e = tokens_per_step * K / (ms_e2e / 1e3)
-        h2d = sum(t.numel() * t.element_size() for t in host[0])
         fpt = 3 * flops_per_token(CFG, Ls)
-        gemm_tflops = (g_fl.value / 1e12) / (g_ms.value / 1e3) if g_ms.value > 0 else 0.0
         traffic = None
         tpath = os.path.join(ROOT, "profiles", "gemm_traffic.json")
         if os.path.exists(tpath):   # dram__bytes_read+write per launch from the committed ncu --set full capture
             traffic = json.load(open(tpath))["mean_dram_bytes_per_launch"]
+        by_kernel = []
+        for cls, name in KERNEL_CLASSES.items():
+            c_ms, c_fl, c_n = r["classes"][cls]
+            tf = (c_fl / 1e12) / (c_ms / 1e3) if c_ms > 0 else 0.0
+            by_kernel.append({"kernel": name, "launches": c_n, "ms_per_step": c_ms / K, "share_of_step": c_ms / ms,
+                              "avg_launch_us": 1e3 * c_ms / c_n if c_n else None, "achieved": tf, "unit": "TFLOP/s",
+                              "frac": tf / peaks["tf_sustained"]})
+        g_ms, g_fl, g_n = r["classes"][0]
+        gemm_tflops = (g_fl / 1e12) / (g_ms / 1e3) if g_ms > 0 else 0.0
         line = {
             "metric": metric, "value": value, "unit": "tokens/s", "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -404,30 +543,57 @@ def main():
                        "global_batch": world * B, "seq_len": Ls, "parallelism": f"dp{world}",
                        "l2": "per-step working set (activations > 10 GB) far exceeds the 126 MB L2; no flush needed",
                        "attention": args.attn, "loss": "torch" if args.torch_loss else "fused", "optimizer": args.optim,
-                       "final_loss": final_loss},
-            "e2e": {"value": e2e, "unit": "tokens/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
+                       "final_loss": r["final_loss"]},
+            "e2e": {"value": e2e, "unit": "tokens/s", "h2d_bytes_per_step": r["h2d"], "d2h_bytes_per_step": 4,
                     "ms_per_step": ms_e2e / K},
-            "gpu_launches": int(launches),
-            "clocks": clocks,
-            "roofline": {"bound": "tensor", "kernel": "gemm_tc_kernel (tcgen05 bf16 GEMM, all launches in the timed region)",
+            "gpu_launches": int(r["launches"]),
+            "host_enqueue_ms_per_step": r["host_ms"] / K,
+            "clocks": r["clocks"],
+            # the dominant kernel class of the step by time; every timed class is in `by_kernel`, the largest single
+            # kernel (by average launch duration) among them in `largest_single_kernel`
+            "roofline": {"bound": "tensor", "kernel": KERNEL_CLASSES[0],
                          "achieved": gemm_tflops, "peak": peaks["tf_sustained"], "unit": "TFLOP/s",
                          "frac": gemm_tflops / peaks["tf_sustained"], "peak_source": peaks["source"] + " sustained",
-                         "traffic": traffic, "launches": g_n.value, "share_of_step": g_ms.value / ms,
-                         "whole_step_tflops": value * fpt / 1e12,
+                         "frac_of_burst_peak": gemm_tflops / peaks["tf_burst"],
+                         "traffic": traffic, "launches": g_n, "share_of_step": g_ms / ms,
+                         "by_kernel": by_kernel,
+                         "largest_single_kernel": max(by_kernel, key=lambda k: k["avg_launch_us"] or 0.0),
+                         "whole_step_tflops": value * fpt / 1e12 / world,
                          "whole_step_frac": value * fpt / 1e12 / peaks["tf_sustained"] / world},
         }
-        if world == 1 and not args.no_decode and args.workload == "cfg2":
-            line["decode"] = decode_leg(model, peaks)
-            if not args.no_cpu_baseline:
-                try:
-                    line["decode"]["cpu_baseline"] = cpu_decode_tokens_per_s()
-                except Exception as e:   # a reported baseline must never cost the measured line
-                    line["decode"]["cpu_baseline"] = {"error": repr(e)}
+        if r["ddp_check"] is not None:
+            line["ddp_check"] = r["ddp_check"]
+    # ---- extra legs (not the quoted metric)
+    if args.workload == "cfg2" and world == 1 and not args.no_decode:
+        dec = decode_leg(model, load_peaks())
+        if not args.no_cpu_baseline:
+            try:
+                dec["cpu_baseline"] = cpu_decode_tokens_per_s()
+            except Exception as e:   # a reported baseline must never cost the measured line
+                dec["cpu_baseline"] = {"error": repr(e)}
+        line["decode"] = dec
+    if args.workload == "cfg2" and not args.no_cfg3_leg:
+        # BASELINE configs[2] (24L/1024d/16h, seq 2048, DDP) as a short extra leg, so that the N = 1, 2, 4, 8 runs of
+        # the driver carry it as well
+        del r, model
+        torch.cuda.empty_cache()
+        c3, L3, Ls3, B3, metric3, label3 = workload("cfg3")
+        r3 = train_leg(args, c3, L3, Ls3, B3, 4, 2, dev, rank, world, lib, with_e2e=False)
+        if rank == 0:
+            v3 = world * B3 * Ls3 * 4 / (r3["ms"] / 1e3)
+            f3 = 3 * flops_per_token(c3, Ls3)
+            line["cfg3"] = {"metric": metric3, "value": v3, "unit": "tokens/s", "ms_per_step": r3["ms"] / 4, "steps": 4,
+                            "warmup": 2, "workload": label3, "global_batch": world * B3, "n_gpus": world,
+                            "whole_step_frac": v3 * f3 / 1e12 / load_peaks()["tf_sustained"] / world,
+                            "final_loss": r3["final_loss"]}
+        del r3
+        torch.cuda.empty_cache()
+    if rank == 0:
         if world == 1 and not args.no_cpu_baseline:
-            tps, cms, threads = cpu_train_tokens_per_s(steps=6, warmup=1, B=1, L=L, cfg=CFG)
-            line["cpu_baseline"] = {"value": tps, "unit": "tokens/s", "cores": threads, "kind": "port",
-                                    "sample": f"6 steps of batch 1 x seq {Ls}, same model, fp32, {threads} threads",
-                                    "ms_per_step": cms}
+            tps, cms, threads, kind = cpu_train_tokens_per_s(steps=6, warmup=1, B=1, L=L, cfg=CFG)
+            line["cpu_baseline"] = {"value": tps, "unit": "tokens/s", "cores": threads, "kind": kind,
+                                    "sample": f"6 steps of batch 1 x seq {Ls}, same model, fp32, fwd+CE+bwd+clip+Adam, "
+                                              f"{threads} threads", "ms_per_step": cms}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

@@ -35,9 +35,9 @@ constexpr int FB_CONTROL_WARP = 8;       // MMA issuer, TMEM alloc
 constexpr int FB_LOAD_WARP = 9;          // TMA loads
 constexpr int FB_THREADS = FB_COMPUTE_THREADS + 64;
 constexpr int FB_OFF_V = 0;
-constexpr int FB_OFF_P = FB_OFF_V + 8192;
-constexpr int FB_OFF_DS = FB_OFF_P + 16384;      // directly behind P: [P | dS]^T is the 128-row A operand of dV
-constexpr int FB_OFF_STAGE = FB_OFF_DS + 16384;  // directly behind dS (rows 64..127 of dK's A operand: never read)
+constexpr int FB_OFF_P = FB_OFF_V + 8192;        // two buffers of [P | dS] (step parity): dS directly behind P, so that
+constexpr int FB_PDS_BYTES = 32768;              // [P | dS]^T is one 128-row A operand; the threads of step st+1 write
+constexpr int FB_OFF_STAGE = FB_OFF_P + 2 * FB_PDS_BYTES;   // theirs while MMA 2 and the TMA store of step st read the other
 // per stage, recompute variant: K | E band | Q | dO   ([K ; Eband] has to be one 256-row B operand, so each stage
 //                                                     carries its own copy of the CTA's K tile)
 //            saved-P variant:   P tile (as saved by the forward pass) | Q | dO
@@ -51,7 +51,7 @@ template <bool SAVED> struct FbStage {
   static constexpr int NS = SAVED ? 3 : 2;               // load stages (what fits next to V, P and dS)
   static constexpr int SMEM = FB_OFF_STAGE + NS * BYTES + 1024;   // + barriers
 };
-static_assert(FB_OFF_P % 1024 == 0 && FB_OFF_STAGE % 1024 == 0 && FbStage<false>::BYTES % 1024 == 0 &&
+static_assert(FB_OFF_P % 1024 == 0 && FB_PDS_BYTES % 1024 == 0 && FB_OFF_STAGE % 1024 == 0 && FbStage<false>::BYTES % 1024 == 0 &&
               FbStage<true>::BYTES % 1024 == 0, "tile alignment");
 static_assert(FbStage<false>::SMEM <= 227 * 1024 && FbStage<true>::SMEM <= 227 * 1024, "shared memory budget");
 constexpr uint32_t FB_TMEM_COLS = 512;
@@ -95,8 +95,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   using ST = FbStage<SAVED>;
   extern __shared__ __align__(1024) uint8_t fb_smem[];
   uint8_t* sV = fb_smem + FB_OFF_V;
-  uint8_t* sP = fb_smem + FB_OFF_P;
-  uint8_t* sdS = fb_smem + FB_OFF_DS;
+  uint8_t* sPdS = fb_smem + FB_OFF_P;   // buffer (st & 1): P at +0, dS at +16384
   uint8_t* sStage = fb_smem + FB_OFF_STAGE;
   constexpr int NS = ST::NS;
   uint64_t* bars = reinterpret_cast<uint64_t*>(fb_smem + FB_OFF_STAGE + NS * ST::BYTES);
@@ -106,9 +105,9 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   uint64_t* m1_done = bars + 7;   // S, R ready
   uint64_t* dp_done = bars + 8;   // dP ready
   uint64_t* a1_done = bars + 9;   // S, R, dP of the step are in registers (256 arrivals)
-  uint64_t* a_done = bars + 10;   // P, dS written (256 arrivals)
-  uint64_t* ds_free = bars + 11;  // the TMA store of the step's dS tile has read shared memory
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 12);
+  uint64_t* a_done = bars + 10;   // [2] P, dS of step st written (barrier st & 1, 256 arrivals)
+  uint64_t* ds_free = bars + 12;  // [2] the TMA store of the step's dS tile has read shared memory (barrier st & 1)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 14);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int kt = blockIdx.x, h = blockIdx.y, bl = blockIdx.z, b = p.b0 + bl;  // bl: index inside the slice (dS scratch)
@@ -129,8 +128,10 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     mbar_init(m1_done, 1);
     mbar_init(dp_done, 1);
     mbar_init(a1_done, FB_COMPUTE_THREADS);
-    mbar_init(a_done, FB_COMPUTE_THREADS);
-    mbar_init(ds_free, 1);
+    for (int k = 0; k < 2; ++k) {
+      mbar_init(&a_done[k], FB_COMPUTE_THREADS);
+      mbar_init(&ds_free[k], 1);
+    }
     fence_mbar_init();
   }
   if (warp == FB_CONTROL_WARP) tmem_alloc(tmem_slot, FB_TMEM_COLS);
@@ -146,7 +147,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     constexpr uint32_t idesc_s = make_idesc_bf16(128, FB_BN, 0, 0);              // dP : K-major x K-major
     constexpr uint32_t idesc_sr = make_idesc_bf16(128, FB_BN + FB_EROWS, 0, 0);  // [S | R]
     constexpr uint32_t idesc_tt = make_idesc_bf16(128, 128, 1, 1);               // [dK | dV] : A^T (MN-major) x B (MN-major)
-    const uint32_t v_addr = smem_u32(sV), p_addr = smem_u32(sP), ds_addr = smem_u32(sdS);
+    const uint32_t v_addr = smem_u32(sV);
     auto issue_mma1 = [&](int st) {
       const uint32_t base = smem_u32(sStage + (st % NS) * ST::BYTES);
       const uint32_t k_addr = base + ST::K, q_addr = base + ST::Q, do_addr = base + ST::DO;
@@ -178,9 +179,10 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         issue_mma1(st + 1);
       }
       FB_TRACE(1, st, 0);
-      mbar_wait(a_done, st & 1);
+      mbar_wait(&a_done[st & 1], (st >> 1) & 1);
       tc_fence_after();
       FB_TRACE(1, st, 1);
+      const uint32_t p_addr = smem_u32(sPdS + (st & 1) * FB_PDS_BYTES);
       const uint32_t q_addr = smem_u32(sStage + (st % NS) * ST::BYTES) + ST::Q;
       const uint32_t acc0 = st > 0 ? 1u : 0u;
       if (elect_one()) {
@@ -237,14 +239,14 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         __syncwarp();
       }
       // the step's dS tile -> scratch (the query-side kernel multiplies it by K, E and Q)
-      mbar_wait(a_done, st & 1);
+      mbar_wait(&a_done[st & 1], (st >> 1) & 1);
       if (elect_one()) {
         const int qi = qi0 + st;
         const int64_t row = (head_row0 + (p.noncausal ? static_cast<int64_t>(qi) * nkt : static_cast<int64_t>(qi) * (qi + 1)) + kt) * FB_BM;
-        tma_store_2d(&tmdS, sdS, 0, static_cast<int>(row));
+        tma_store_2d(&tmdS, sPdS + (st & 1) * FB_PDS_BYTES + 16384, 0, static_cast<int>(row));
         bulk_commit();
         bulk_wait_read_all();
-        mbar_arrive(ds_free);
+        mbar_arrive(&ds_free[st & 1]);
       }
       __syncwarp();
     }
@@ -370,15 +372,15 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         }
       }
       if (warp == 0) FB_TRACE(0, st, 3);
-      // MMA 2 and the TMA store of the previous step must have read P / dS
-      if (st > 0) {
-        mbar_wait(&m2_done[(st - 1) % NS], ((st - 1) / NS) & 1);
-        mbar_wait(ds_free, (st - 1) & 1);
+      // MMA 2 and the TMA store of step st-2 must have read this buffer of P / dS
+      if (st > 1) {
+        mbar_wait(&m2_done[(st - 2) % NS], ((st - 2) / NS) & 1);
+        mbar_wait(&ds_free[st & 1], ((st - 2) >> 1) & 1);
       }
       // P and dS rows: UMMA SWIZZLE_128B rows of 128 B (chunk kc of row a at position kc ^ (a & 7))
       {
-        uint8_t* prow = sP + a * 128;
-        uint8_t* drow = sdS + a * 128;
+        uint8_t* prow = sPdS + (st & 1) * FB_PDS_BYTES + a * 128;
+        uint8_t* drow = prow + 16384;
 #pragma unroll
         for (int n = 0; n < 4; ++n) {
           const int pos = (((4 * half + n) ^ (a & 7))) << 4;
@@ -389,7 +391,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       if (warp == 0) FB_TRACE(0, st, 4);
       fence_proxy_async_smem();
       tc_fence_before();
-      mbar_arrive(a_done);
+      mbar_arrive(&a_done[st & 1]);
       if (warp == 0) FB_TRACE(0, st, 5);
     }
 
