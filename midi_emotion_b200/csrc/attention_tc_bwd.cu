@@ -34,8 +34,8 @@ constexpr int FB_COMPUTE_THREADS = 256;  // 8 warps: warp w and w+4 share TMEM l
 constexpr int FB_CONTROL_WARP = 8;       // MMA issuer, TMEM alloc
 constexpr int FB_LOAD_WARP = 9;          // TMA loads
 constexpr int FB_THREADS = FB_COMPUTE_THREADS + 64;
-constexpr int FB_OFF_V = 0;
-constexpr int FB_OFF_P = FB_OFF_V + 8192;        // two buffers of [P | dS] (step parity): dS directly behind P, so that
+constexpr int FB_OFF_V = 0;                     // two V tiles (item parity)
+constexpr int FB_OFF_P = FB_OFF_V + 2 * 8192;       // two buffers of [P | dS] (step parity): dS directly behind P, so that
 constexpr int FB_PDS_BYTES = 32768;              // [P | dS]^T is one 128-row A operand; the threads of step st+1 write
 constexpr int FB_OFF_STAGE = FB_OFF_P + 2 * FB_PDS_BYTES;   // theirs while MMA 2 and the TMA store of step st read the other
 // per stage, recompute variant: K | E band | Q | dO   ([K ; Eband] has to be one 256-row B operand, so each stage
@@ -70,7 +70,7 @@ struct FbParams {
   float scale_log2, scale;
   int noncausal;     // ME_ATTN_NONCAUSAL: every query tile, every key < L visible
   int tiles_per_head;  // dS scratch: tile (qi, kt) of head (b, h) starts at row ((b H + h) tiles_per_head + index) 128
-  int b0;              // first sequence of this launch's slice of the batch (blockIdx.z counts from it)
+  int b0, nb;          // this launch's slice of the batch: sequences b0 .. b0 + nb - 1
   const float* m_tiles;  // SAVED: exponent offsets of the saved probability tiles
   long long* trace;      // tuning builds (-DME_ATTN_TRACE)
   int saved_tiles_per_head;
@@ -86,6 +86,15 @@ extern long long* g_attn_trace;
 #define FB_TRACE(role, st, k) do { } while (0)
 #endif
 
+// One work item = one 64-key tile of one (sequence, head); the kernel is persistent: CTA c works through the items
+// c, c + grid, c + 2 grid, ... with every per-step barrier and buffer index running on a global step counter, so the
+// loads of the next item are in flight while the current one finishes and nothing is set up or torn down per item
+// (the items are short -- 4.5 steps on average at L = 1024 -- and the per-CTA prologue / epilogue of the one-item
+// version cost a third of the kernel).
+struct FbItem {
+  int kt, h, bl, b, j0, qi0, nsteps;
+};
+
 template <int DH, bool SAVED>
 __global__ void __launch_bounds__(FB_THREADS, 1)
 attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
@@ -94,33 +103,59 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   constexpr int HC = DH / 2;          // accumulator columns handled by each of the two threads of a row
   using ST = FbStage<SAVED>;
   extern __shared__ __align__(1024) uint8_t fb_smem[];
-  uint8_t* sV = fb_smem + FB_OFF_V;
-  uint8_t* sPdS = fb_smem + FB_OFF_P;   // buffer (st & 1): P at +0, dS at +16384
+  uint8_t* sV = fb_smem + FB_OFF_V;       // two buffers (item parity), 8 KB each
+  uint8_t* sPdS = fb_smem + FB_OFF_P;     // buffer (g & 1): P at +0, dS at +16384
   uint8_t* sStage = fb_smem + FB_OFF_STAGE;
   constexpr int NS = ST::NS;
   uint64_t* bars = reinterpret_cast<uint64_t*>(fb_smem + FB_OFF_STAGE + NS * ST::BYTES);
-  uint64_t* v_full = bars + 0;
-  uint64_t* ld_full = bars + 1;   // [NS] per step: (K, the band of E | the saved P tile), Q and dO
-  uint64_t* m2_done = bars + 4;   // [NS] dV, dK accumulated: the step's stage, P and dS are free
-  uint64_t* m1_done = bars + 7;   // S, R ready
-  uint64_t* dp_done = bars + 8;   // dP ready
-  uint64_t* a1_done = bars + 9;   // S, R, dP of the step are in registers (256 arrivals)
-  uint64_t* a_done = bars + 10;   // [2] P, dS of step st written (barrier st & 1, 256 arrivals)
-  uint64_t* ds_free = bars + 12;  // [2] the TMA store of the step's dS tile has read shared memory (barrier st & 1)
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 14);
+  uint64_t* v_full = bars + 0;    // [2] V of an item (item parity)
+  uint64_t* ld_full = bars + 2;   // [NS] per step: (K, the band of E | the saved P tile), Q and dO
+  uint64_t* m2_done = bars + 5;   // [NS] dV, dK accumulated: the step's stage, P and dS are free
+  uint64_t* m1_done = bars + 8;   // S, R ready
+  uint64_t* dp_done = bars + 9;   // dP ready
+  uint64_t* a1_done = bars + 10;  // S, R, dP of the step are in registers (256 arrivals)
+  uint64_t* a_done = bars + 11;   // [2] P, dS of step g written (barrier g & 1, 256 arrivals)
+  uint64_t* ds_free = bars + 13;  // [2] the TMA store of the step's dS tile has read shared memory (barrier g & 1)
+  uint64_t* dkv_read = bars + 15; // dK / dV of an item are out of tensor memory (256 arrivals)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 16);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int kt = blockIdx.x, h = blockIdx.y, bl = blockIdx.z, b = p.b0 + bl;  // bl: index inside the slice (dS scratch)
-  const int j0 = kt * FB_BN;
   const int nq = (p.L + FB_BM - 1) / FB_BM;
-  const int qi0 = p.noncausal ? 0 : j0 / FB_BM;
-  const int nsteps = nq - qi0;
-  const bool tr = p.trace != nullptr && kt == 0 && h == 0 && bl == 0 && lane == 0;
+  const int nkt = (p.L + FB_BN - 1) / FB_BN;
+  const int n_items = nkt * p.H * p.nb;
+  // item i -> (kt, h, bl): consecutive items are the key tiles of one head (their CTAs run at the same time and share
+  // Q / dO through the L2); the key tile is skewed by the head index so that the round-robin over CTAs hands every
+  // CTA the same mix of long (early keys) and short (late keys) items
+  auto get_item = [&](int i) -> FbItem {
+    FbItem it;
+    const int grp = i / nkt;
+    it.kt = (i % nkt + grp) % nkt;
+    it.h = grp % p.H;
+    it.bl = grp / p.H;
+    it.b = p.b0 + it.bl;
+    it.j0 = it.kt * FB_BN;
+    it.qi0 = p.noncausal ? 0 : it.j0 / FB_BM;
+    it.nsteps = nq - it.qi0;
+    return it;
+  };
+  auto tile_index = [&](const FbItem& it, int st, bool saved_layout) -> int64_t {
+    const int qi = it.qi0 + st;
+    if (saved_layout)
+      return (static_cast<int64_t>(it.b) * p.H + it.h) * p.saved_tiles_per_head +
+             (p.noncausal ? static_cast<int64_t>(qi) * nkt : static_cast<int64_t>(qi) * (qi + 1)) + it.kt;
+    return (static_cast<int64_t>(it.bl) * p.H + it.h) * p.tiles_per_head +
+           (p.noncausal ? static_cast<int64_t>(qi) * nkt : static_cast<int64_t>(qi) * (qi + 1)) + it.kt;
+  };
+  const bool tr = p.trace != nullptr && blockIdx.x == 0 && lane == 0;
   (void)tr;
 
   if (tid == 0) {
     if ((smem_u32(fb_smem) & 1023u) != 0) __trap();
-    mbar_init(v_full, 1);
+    for (int k = 0; k < 2; ++k) {
+      mbar_init(&v_full[k], 1);
+      mbar_init(&a_done[k], FB_COMPUTE_THREADS);
+      mbar_init(&ds_free[k], 1);
+    }
     for (int k = 0; k < NS; ++k) {
       mbar_init(&ld_full[k], 1);
       mbar_init(&m2_done[k], 1);
@@ -128,10 +163,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     mbar_init(m1_done, 1);
     mbar_init(dp_done, 1);
     mbar_init(a1_done, FB_COMPUTE_THREADS);
-    for (int k = 0; k < 2; ++k) {
-      mbar_init(&a_done[k], FB_COMPUTE_THREADS);
-      mbar_init(&ds_free[k], 1);
-    }
+    mbar_init(dkv_read, FB_COMPUTE_THREADS);
     fence_mbar_init();
   }
   if (warp == FB_CONTROL_WARP) tmem_alloc(tmem_slot, FB_TMEM_COLS);
@@ -147,10 +179,10 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     constexpr uint32_t idesc_s = make_idesc_bf16(128, FB_BN, 0, 0);              // dP : K-major x K-major
     constexpr uint32_t idesc_sr = make_idesc_bf16(128, FB_BN + FB_EROWS, 0, 0);  // [S | R]
     constexpr uint32_t idesc_tt = make_idesc_bf16(128, 128, 1, 1);               // [dK | dV] : A^T (MN-major) x B (MN-major)
-    const uint32_t v_addr = smem_u32(sV);
-    auto issue_mma1 = [&](int st) {
-      const uint32_t base = smem_u32(sStage + (st % NS) * ST::BYTES);
+    auto issue_mma1 = [&](int g, int item_n) {
+      const uint32_t base = smem_u32(sStage + (g % NS) * ST::BYTES);
       const uint32_t k_addr = base + ST::K, q_addr = base + ST::Q, do_addr = base + ST::DO;
+      const uint32_t v_addr = smem_u32(sV + (item_n & 1) * 8192);
       if (elect_one()) {
         if (!SAVED) {
 #pragma unroll
@@ -167,57 +199,55 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       }
       __syncwarp();
     };
-    mbar_wait(v_full, 0);
-    mbar_wait(&ld_full[0], 0);
-    tc_fence_after();
-    issue_mma1(0);
-    for (int st = 0; st < nsteps; ++st) {
-      if (st + 1 < nsteps) {
-        mbar_wait(&ld_full[(st + 1) % NS], ((st + 1) / NS) & 1);
-        mbar_wait(a1_done, st & 1);   // S, R, dP of step st are out of tensor memory
-        tc_fence_after();
-        issue_mma1(st + 1);
-      }
-      FB_TRACE(1, st, 0);
-      mbar_wait(&a_done[st & 1], (st >> 1) & 1);
+    int g = 0, n = 0;
+    // MMA 1 of a step is issued one step ahead of its MMA 2: `pend_*` is the step whose MMA 1 comes next
+    int i_next = blockIdx.x;
+    FbItem nx = i_next < n_items ? get_item(i_next) : FbItem{};
+    int nx_st = 0, nx_n = 0, nx_g = 0;
+    auto issue_next_mma1 = [&]() {   // MMA 1 of (item nx_n, step nx_st), global step nx_g; then advance
+      if (i_next >= n_items) return;
+      if (nx_st == 0) mbar_wait(&v_full[nx_n & 1], (nx_n >> 1) & 1);
+      mbar_wait(&ld_full[nx_g % NS], (nx_g / NS) & 1);
+      if (nx_g > 0) mbar_wait(a1_done, (nx_g - 1) & 1);   // S, R, dP of the previous step are out of tensor memory
       tc_fence_after();
-      FB_TRACE(1, st, 1);
-      const uint32_t p_addr = smem_u32(sPdS + (st & 1) * FB_PDS_BYTES);
-      const uint32_t q_addr = smem_u32(sStage + (st % NS) * ST::BYTES) + ST::Q;
-      const uint32_t acc0 = st > 0 ? 1u : 0u;
-      if (elect_one()) {
-        // [. | dV ; dK | .] += [P | dS]^T [Q | dO]: rows 0..63 of the accumulator are P^T (keys), rows 64..127 dS^T;
-        // columns 0..63 multiply Q, columns 64..127 dO.  dK = lanes 64..127 x columns 0..63, dV = lanes 0..63 x
-        // columns 64..127; the other two blocks are never read.
-#pragma unroll
-        for (int k = 0; k < 8; ++k)
-          umma_bf16(tmem_base + FB_COL_DK, make_smem_desc_sw128(p_addr + k * 2048, 16384, 1024),
-                    make_smem_desc_sw128(q_addr + k * 2048, 16384, 1024), idesc_tt, (k > 0) ? 1u : acc0);
-        umma_commit(&m2_done[st % NS]);
+      issue_mma1(nx_g, nx_n);
+      ++nx_g;
+      if (++nx_st == nx.nsteps) {
+        nx_st = 0;
+        ++nx_n;
+        i_next += gridDim.x;
+        if (i_next < n_items) nx = get_item(i_next);
       }
-      __syncwarp();
-      FB_TRACE(1, st, 2);
+    };
+    issue_next_mma1();
+    for (int i = blockIdx.x; i < n_items; i += gridDim.x, ++n) {
+      const FbItem it = get_item(i);
+      for (int st = 0; st < it.nsteps; ++st, ++g) {
+        issue_next_mma1();   // MMA 1 of step g+1 (possibly the first step of the next item)
+        FB_TRACE(1, g, 0);
+        mbar_wait(&a_done[g & 1], (g >> 1) & 1);
+        if (st == 0 && n > 0) mbar_wait(dkv_read, (n - 1) & 1);   // the previous item's dK / dV have been read out
+        tc_fence_after();
+        FB_TRACE(1, g, 1);
+        const uint32_t p_addr = smem_u32(sPdS + (g & 1) * FB_PDS_BYTES);
+        const uint32_t q_addr = smem_u32(sStage + (g % NS) * ST::BYTES) + ST::Q;
+        const uint32_t acc0 = st > 0 ? 1u : 0u;
+        if (elect_one()) {
+          // [. | dV ; dK | .] += [P | dS]^T [Q | dO]: rows 0..63 of the accumulator are P^T (keys), rows 64..127
+          // dS^T; columns 0..63 multiply Q, columns 64..127 dO.  dK = lanes 64..127 x columns 0..63, dV = lanes
+          // 0..63 x columns 64..127; the other two blocks are never read.
+#pragma unroll
+          for (int k = 0; k < 8; ++k)
+            umma_bf16(tmem_base + FB_COL_DK, make_smem_desc_sw128(p_addr + k * 2048, 16384, 1024),
+                      make_smem_desc_sw128(q_addr + k * 2048, 16384, 1024), idesc_tt, (k > 0) ? 1u : acc0);
+          umma_commit(&m2_done[g % NS]);
+        }
+        __syncwarp();
+        FB_TRACE(1, g, 2);
+      }
     }
   } else if (warp == FB_LOAD_WARP) {
-    // ======================= TMA loads =======================
-    auto load_step = [&](int st) {
-      uint8_t* base = sStage + (st % NS) * ST::BYTES;
-      uint64_t* bar = &ld_full[st % NS];
-      const int qi = qi0 + st;
-      const int i0 = qi * FB_BM;
-      mbar_arrive_expect_tx(bar, ST::TX);
-      if (SAVED) {
-        const int64_t tile = (static_cast<int64_t>(b) * p.H + h) * p.saved_tiles_per_head +
-                             (p.noncausal ? static_cast<int64_t>(qi) * ((p.L + FB_BN - 1) / FB_BN)
-                                          : static_cast<int64_t>(qi) * (qi + 1)) + kt;
-        tma_load_2d(&tmK, bar, base + ST::P, 0, static_cast<int>(tile * FB_BM));   // (tmK: the saved-P tile map)
-      } else {
-        tma_load_4d(&tmK, bar, base + ST::K, 0, h, j0, b);
-        tma_load_2d(&tmE, bar, base + ST::E, 0, p.max_seq - FB_BM - (i0 - j0));
-      }
-      tma_load_4d(&tmQ, bar, base + ST::Q, 0, h, i0, b);
-      tma_load_4d(&tmdO, bar, base + ST::DO, 0, h, i0, b);
-    };
+    // ======================= TMA loads and the dS stores =======================
     if (elect_one()) {
       tma_prefetch_desc(&tmQ);
       tma_prefetch_desc(&tmK);
@@ -225,30 +255,65 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       tma_prefetch_desc(&tmdO);
       tma_prefetch_desc(&tmE);
       tma_prefetch_desc(&tmdS);
-      mbar_arrive_expect_tx(v_full, 8192);
-      tma_load_4d(&tmV, v_full, sV, 0, h, j0, b);
-      for (int st = 0; st < NS && st < nsteps; ++st) load_step(st);
     }
     __syncwarp();
-    const int nkt = (p.L + FB_BN - 1) / FB_BN;
-    const int64_t head_row0 = (static_cast<int64_t>(bl) * p.H + h) * p.tiles_per_head;
-    for (int st = 0; st < nsteps; ++st) {
-      if (st >= 1 && st + NS - 1 < nsteps) {
-        mbar_wait(&m2_done[(st - 1) % NS], ((st - 1) / NS) & 1);   // the MMAs of step st-1 have read its stage
-        if (elect_one()) load_step(st + NS - 1);
-        __syncwarp();
+    // the loads run NS - 1 steps ahead of the stores: `ld_*` walks the (item, step) sequence for the loads
+    int ld_i = blockIdx.x, ld_n = 0, ld_st = 0, ld_g = 0;
+    FbItem ld = ld_i < n_items ? get_item(ld_i) : FbItem{};
+    int last_g_of_item[2] = {-1, -1};   // global index of the last step of items n-1, n-2 (by parity): V buffer reuse
+    auto load_next = [&]() {
+      if (ld_i >= n_items) return;
+      // stage (ld_g % NS) was last read by the MMAs of step ld_g - NS
+      if (ld_g >= NS) mbar_wait(&m2_done[ld_g % NS], ((ld_g - NS) / NS) & 1);
+      if (ld_st == 0) {
+        // V buffer (ld_n & 1) was last read by dP of the last step of item ld_n - 2
+        const int gl = last_g_of_item[ld_n & 1];
+        if (ld_n >= 2 && gl > ld_g - NS) mbar_wait(&m2_done[gl % NS], (gl / NS) & 1);
+        last_g_of_item[ld_n & 1] = ld_g + ld.nsteps - 1;
       }
-      // the step's dS tile -> scratch (the query-side kernel multiplies it by K, E and Q)
-      mbar_wait(&a_done[st & 1], (st >> 1) & 1);
       if (elect_one()) {
-        const int qi = qi0 + st;
-        const int64_t row = (head_row0 + (p.noncausal ? static_cast<int64_t>(qi) * nkt : static_cast<int64_t>(qi) * (qi + 1)) + kt) * FB_BM;
-        tma_store_2d(&tmdS, sPdS + (st & 1) * FB_PDS_BYTES + 16384, 0, static_cast<int>(row));
-        bulk_commit();
-        bulk_wait_read_all();
-        mbar_arrive(&ds_free[st & 1]);
+        if (ld_st == 0) {
+          mbar_arrive_expect_tx(&v_full[ld_n & 1], 8192);
+          tma_load_4d(&tmV, &v_full[ld_n & 1], sV + (ld_n & 1) * 8192, 0, ld.h, ld.j0, ld.b);
+        }
+        uint8_t* base = sStage + (ld_g % NS) * ST::BYTES;
+        uint64_t* bar = &ld_full[ld_g % NS];
+        const int i0 = (ld.qi0 + ld_st) * FB_BM;
+        mbar_arrive_expect_tx(bar, ST::TX);
+        if (SAVED) {
+          tma_load_2d(&tmK, bar, base + ST::P, 0, static_cast<int>(tile_index(ld, ld_st, true) * FB_BM));  // (tmK: saved-P map)
+        } else {
+          tma_load_4d(&tmK, bar, base + ST::K, 0, ld.h, ld.j0, ld.b);
+          tma_load_2d(&tmE, bar, base + ST::E, 0, p.max_seq - FB_BM - (i0 - ld.j0));
+        }
+        tma_load_4d(&tmQ, bar, base + ST::Q, 0, ld.h, i0, ld.b);
+        tma_load_4d(&tmdO, bar, base + ST::DO, 0, ld.h, i0, ld.b);
       }
       __syncwarp();
+      ++ld_g;
+      if (++ld_st == ld.nsteps) {
+        ld_st = 0;
+        ++ld_n;
+        ld_i += gridDim.x;
+        if (ld_i < n_items) ld = get_item(ld_i);
+      }
+    };
+    for (int k = 0; k < NS - 1; ++k) load_next();
+    int g = 0;
+    for (int i = blockIdx.x; i < n_items; i += gridDim.x) {
+      const FbItem it = get_item(i);
+      for (int st = 0; st < it.nsteps; ++st, ++g) {
+        load_next();    // the loads of step g + NS - 1
+        // the step's dS tile -> scratch (the query-side kernel multiplies it by K, E and Q)
+        mbar_wait(&a_done[g & 1], (g >> 1) & 1);
+        if (elect_one()) {
+          tma_store_2d(&tmdS, sPdS + (g & 1) * FB_PDS_BYTES + 16384, 0, static_cast<int>(tile_index(it, st, false) * FB_BM));
+          bulk_commit();
+          bulk_wait_read_all();
+          mbar_arrive(&ds_free[g & 1]);
+        }
+        __syncwarp();
+      }
     }
     if (elect_one()) bulk_wait_all();
     __syncwarp();
@@ -258,153 +323,31 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     const int a = quarter * 32 + lane;   // query row inside the tile == TMEM lane
     const int shift = 31 - lane;
     const uint32_t t_lane = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16);
-    const uint8_t* kp = p.keypad ? p.keypad + static_cast<int64_t>(b) * p.keypad_ld : nullptr;
-    uint32_t kpm = 0;  // key-pad bits of this thread's 32 keys
-    if (kp || p.noncausal) {  // (keys past the sequence only matter without the causal predicate)
-      const int j = j0 + 32 * half + lane;
-      kpm = __ballot_sync(0xffffffffu, j >= p.L || (kp && kp[j] != 0));
-    }
     const float cs = p.scale_log2;
 
     // the per-row scalars of a step (log-sum-exp, D, and the exponent offset of the saved tile) come from global
     // memory: they are fetched one step ahead, their latency (~1000 cycles each) used to sit on every step
-    auto saved_tile = [&](int st) -> int64_t {
-      const int qi = qi0 + st;
-      return (static_cast<int64_t>(b) * p.H + h) * p.saved_tiles_per_head +
-             (p.noncausal ? static_cast<int64_t>(qi) * ((p.L + FB_BN - 1) / FB_BN) : static_cast<int64_t>(qi) * (qi + 1)) + kt;
-    };
     float nxt_l = -INFINITY, nxt_D = 0.f, nxt_m = 0.f;
-    auto fetch_row_scalars = [&](int st) {
-      const int i = (qi0 + st) * FB_BM + a;
+    auto fetch_row_scalars = [&](const FbItem& it, int st) {
+      const int i = (it.qi0 + st) * FB_BM + a;
       nxt_l = -INFINITY;
       nxt_D = 0.f;
       nxt_m = 0.f;
-      if (st < nsteps && i < p.L) {
-        const int64_t stat = (static_cast<int64_t>(b) * p.H + h) * p.L + i;
+      if (i < p.L) {
+        const int64_t stat = (static_cast<int64_t>(it.b) * p.H + it.h) * p.L + i;
         nxt_l = p.lse[stat];
         nxt_D = p.dsum[stat];
       }
-      if (SAVED && st < nsteps) nxt_m = p.m_tiles[saved_tile(st) * FB_BM + a];
+      if (SAVED) nxt_m = p.m_tiles[tile_index(it, st, true) * FB_BM + a];
     };
-    fetch_row_scalars(0);
-
-    for (int st = 0; st < nsteps; ++st) {
-      const uint32_t ph = st & 1;
-      const int i0 = (qi0 + st) * FB_BM;
-      const int i = i0 + a;
-      const bool row_ok = i < p.L;
-      const float l_nat = nxt_l, Di = nxt_D, m_saved = nxt_m;
-      fetch_row_scalars(st + 1);
-      const int lim = p.noncausal ? 31 : i - j0 - 32 * half;  // this thread's columns bb <= lim are causal-visible
-      uint32_t vm = lim >= 31 ? 0xffffffffu : (lim < 0 ? 0u : ((2u << lim) - 1u));
-      vm &= ~kpm;
-
-      const float lse2 = (!row_ok || l_nat == -INFINITY) ? INFINITY : l_nat * 1.4426950408889634f;
-      if (warp == 0) FB_TRACE(0, st, 0);
-
-      uint32_t pw[16], dw[16];  // bf16x2 words of P[a, 32h..] and dS[a, 32h..]
-      {
-        float pe[32];
-        if (SAVED) {
-          // P = p_saved * exp2(m_saved - lse): the forward pass formed p_saved = exp2(x c - m_saved), masks included
-          const float cfac = fast_exp2(m_saved - lse2);
-          mbar_wait(&ld_full[st % NS], (st / NS) & 1);
-          const uint8_t* prow_in = sStage + (st % NS) * ST::BYTES + ST::P + a * 128;
-#pragma unroll
-          for (int n = 0; n < 4; ++n) {
-            const uint4 u = *reinterpret_cast<const uint4*>(prow_in + (((4 * half + n) ^ (a & 7)) << 4));
-            const uint32_t wv[4] = {u.x, u.y, u.z, u.w};
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              pe[8 * n + 2 * e] = __uint_as_float(wv[e] << 16) * cfac;
-              pe[8 * n + 2 * e + 1] = __uint_as_float(wv[e] & 0xFFFF0000u) * cfac;
-            }
-          }
-          (void)vm;
-          (void)cs;
-          (void)ph;
-        } else {
-          mbar_wait(m1_done, ph);
-          tc_fence_after();
-          uint32_t sv[32], rv[64];
-          tmem_ld32(t_lane + FB_COL_S + 32 * half, sv);
-          tmem_ld64(t_lane + FB_COL_R + 96 - 32 * quarter + 32 * half, rv);
-          tc_wait_ld();
-          skew_select(rv, shift);
-          // only the tiles on the diagonal (and rows past the sequence / pad keys) need the mask: a warp-uniform
-          // branch keeps 96 ALU-pipe instructions out of the common case
-          if (__all_sync(0xffffffffu, vm == 0xffffffffu)) {
-#pragma unroll
-            for (int bb = 0; bb < 32; ++bb)
-              pe[bb] = fast_exp2(fmaf(__uint_as_float(sv[bb]) + __uint_as_float(rv[bb]), cs, -lse2));
-          } else {
-#pragma unroll
-            for (int bb = 0; bb < 32; ++bb) {
-              const float x = __uint_as_float(sv[bb]) + __uint_as_float(rv[bb]);
-              const float e = fast_exp2(fmaf(x, cs, -lse2));
-              pe[bb] = ((vm >> bb) & 1u) ? e : 0.f;
-            }
-          }
-        }
-#pragma unroll
-        for (int bb = 0; bb < 32; bb += 2) {
-          __nv_bfloat162 ph2 = __floats2bfloat162_rn(pe[bb], pe[bb + 1]);
-          pw[bb / 2] = *reinterpret_cast<uint32_t*>(&ph2);
-        }
-        if (warp == 0) FB_TRACE(0, st, 1);
-        mbar_wait(dp_done, ph);  // dP was issued behind [S | R]: it lands while P is being formed
-        tc_fence_after();
-        if (warp == 0) FB_TRACE(0, st, 2);
-        {
-          uint32_t dpv[32];
-          tmem_ld32(t_lane + FB_COL_DP + 32 * half, dpv);
-          tc_wait_ld();
-          tc_fence_before();
-          mbar_arrive(a1_done);  // S, R, dP are in registers: MMA 1 of the next step may overwrite them
-          const float nds = -Di * p.scale;
-#pragma unroll
-          for (int bb = 0; bb < 32; bb += 2) {
-            const float d0 = pe[bb] * fmaf(__uint_as_float(dpv[bb]), p.scale, nds);
-            const float d1 = pe[bb + 1] * fmaf(__uint_as_float(dpv[bb + 1]), p.scale, nds);
-            __nv_bfloat162 dh2 = __floats2bfloat162_rn(d0, d1);
-            dw[bb / 2] = *reinterpret_cast<uint32_t*>(&dh2);
-          }
-        }
-      }
-      if (warp == 0) FB_TRACE(0, st, 3);
-      // MMA 2 and the TMA store of step st-2 must have read this buffer of P / dS
-      if (st > 1) {
-        mbar_wait(&m2_done[(st - 2) % NS], ((st - 2) / NS) & 1);
-        mbar_wait(&ds_free[st & 1], ((st - 2) >> 1) & 1);
-      }
-      // P and dS rows: UMMA SWIZZLE_128B rows of 128 B (chunk kc of row a at position kc ^ (a & 7))
-      {
-        uint8_t* prow = sPdS + (st & 1) * FB_PDS_BYTES + a * 128;
-        uint8_t* drow = prow + 16384;
-#pragma unroll
-        for (int n = 0; n < 4; ++n) {
-          const int pos = (((4 * half + n) ^ (a & 7))) << 4;
-          *reinterpret_cast<uint4*>(prow + pos) = make_uint4(pw[4 * n], pw[4 * n + 1], pw[4 * n + 2], pw[4 * n + 3]);
-          *reinterpret_cast<uint4*>(drow + pos) = make_uint4(dw[4 * n], dw[4 * n + 1], dw[4 * n + 2], dw[4 * n + 3]);
-        }
-      }
-      if (warp == 0) FB_TRACE(0, st, 4);
-      fence_proxy_async_smem();
-      tc_fence_before();
-      mbar_arrive(&a_done[st & 1]);
-      if (warp == 0) FB_TRACE(0, st, 5);
-    }
-
-    // dK / dV: rows 0..63 of the accumulators (TMEM lanes 0..63: quarters 0 and 1), columns split by half
-    mbar_wait(&m2_done[(nsteps - 1) % NS], ((nsteps - 1) / NS) & 1);
-    tc_fence_after();
-    {
-      // lanes 0..63 (quarters 0, 1) hold dV rows, lanes 64..127 (quarters 2, 3) dK rows, of key j0 + (a & 63)
+    // dK / dV of an item: lanes 0..63 (quarters 0, 1) hold dV rows, lanes 64..127 (quarters 2, 3) dK rows, of key
+    // j0 + (a & 63); read out by the threads during the first step of the NEXT item (or after the last one)
+    auto write_dkv = [&](const FbItem& it) {
       const bool is_dv = quarter < 2;
-      const int j = j0 + (a & 63);
+      const int j = it.j0 + (a & 63);
       const bool key_ok = j < p.L;
-      bf16* row = is_dv ? p.dv + static_cast<int64_t>(b) * p.v_sb + static_cast<int64_t>(j) * p.v_sj + h * p.v_sh + half * HC
-                        : p.dk + static_cast<int64_t>(b) * p.k_sb + static_cast<int64_t>(j) * p.k_sj + h * p.k_sh + half * HC;
+      bf16* row = is_dv ? p.dv + static_cast<int64_t>(it.b) * p.v_sb + static_cast<int64_t>(j) * p.v_sj + it.h * p.v_sh + half * HC
+                        : p.dk + static_cast<int64_t>(it.b) * p.k_sb + static_cast<int64_t>(j) * p.k_sj + it.h * p.k_sh + half * HC;
       const uint32_t col = (is_dv ? FB_COL_DV : FB_COL_DK) + half * HC;
 #pragma unroll
       for (int c0 = 0; c0 < HC; c0 += 8) {
@@ -419,6 +362,142 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
           *reinterpret_cast<uint4*>(row + c0) = u;
         }
       }
+      tc_fence_before();
+      mbar_arrive(dkv_read);
+    };
+
+    int g = 0, n = 0;
+    FbItem prev{};
+    int prev_last_g = -1;
+    if (static_cast<int>(blockIdx.x) < n_items) fetch_row_scalars(get_item(blockIdx.x), 0);
+    for (int i = blockIdx.x; i < n_items; i += gridDim.x, ++n) {
+      const FbItem it = get_item(i);
+      const uint8_t* kp = p.keypad ? p.keypad + static_cast<int64_t>(it.b) * p.keypad_ld : nullptr;
+      uint32_t kpm = 0;  // key-pad bits of this thread's 32 keys
+      if (kp || p.noncausal) {  // (keys past the sequence only matter without the causal predicate)
+        const int j = it.j0 + 32 * half + lane;
+        kpm = __ballot_sync(0xffffffffu, j >= p.L || (kp && kp[j] != 0));
+      }
+      for (int st = 0; st < it.nsteps; ++st, ++g) {
+        const uint32_t ph = g & 1;
+        const int i0 = (it.qi0 + st) * FB_BM;
+        const int irow = i0 + a;
+        const bool row_ok = irow < p.L;
+        const float l_nat = nxt_l, Di = nxt_D, m_saved = nxt_m;
+        if (st + 1 < it.nsteps) fetch_row_scalars(it, st + 1);
+        else if (i + static_cast<int>(gridDim.x) < n_items) fetch_row_scalars(get_item(i + gridDim.x), 0);
+        const int lim = p.noncausal ? 31 : irow - it.j0 - 32 * half;  // this thread's columns bb <= lim are causal-visible
+        uint32_t vm = lim >= 31 ? 0xffffffffu : (lim < 0 ? 0u : ((2u << lim) - 1u));
+        vm &= ~kpm;
+
+        const float lse2 = (!row_ok || l_nat == -INFINITY) ? INFINITY : l_nat * 1.4426950408889634f;
+        if (warp == 0) FB_TRACE(0, g, 0);
+
+        uint32_t pw[16], dw[16];  // bf16x2 words of P[a, 32h..] and dS[a, 32h..]
+        {
+          float pe[32];
+          if (SAVED) {
+            // P = p_saved * exp2(m_saved - lse): the forward pass formed p_saved = exp2(x c - m_saved), masks included
+            const float cfac = fast_exp2(m_saved - lse2);
+            mbar_wait(&ld_full[g % NS], (g / NS) & 1);
+            const uint8_t* prow_in = sStage + (g % NS) * ST::BYTES + ST::P + a * 128;
+#pragma unroll
+            for (int nn = 0; nn < 4; ++nn) {
+              const uint4 u = *reinterpret_cast<const uint4*>(prow_in + (((4 * half + nn) ^ (a & 7)) << 4));
+              const uint32_t wv[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                pe[8 * nn + 2 * e] = __uint_as_float(wv[e] << 16) * cfac;
+                pe[8 * nn + 2 * e + 1] = __uint_as_float(wv[e] & 0xFFFF0000u) * cfac;
+              }
+            }
+            (void)vm;
+            (void)cs;
+            (void)shift;
+          } else {
+            mbar_wait(m1_done, ph);
+            tc_fence_after();
+            uint32_t sv[32], rv[64];
+            tmem_ld32(t_lane + FB_COL_S + 32 * half, sv);
+            tmem_ld64(t_lane + FB_COL_R + 96 - 32 * quarter + 32 * half, rv);
+            tc_wait_ld();
+            skew_select(rv, shift);
+            // only the tiles on the diagonal (and rows past the sequence / pad keys) need the mask: a warp-uniform
+            // branch keeps 96 ALU-pipe instructions out of the common case
+            if (__all_sync(0xffffffffu, vm == 0xffffffffu)) {
+#pragma unroll
+              for (int bb = 0; bb < 32; ++bb)
+                pe[bb] = fast_exp2(fmaf(__uint_as_float(sv[bb]) + __uint_as_float(rv[bb]), cs, -lse2));
+            } else {
+#pragma unroll
+              for (int bb = 0; bb < 32; ++bb) {
+                const float x = __uint_as_float(sv[bb]) + __uint_as_float(rv[bb]);
+                const float e = fast_exp2(fmaf(x, cs, -lse2));
+                pe[bb] = ((vm >> bb) & 1u) ? e : 0.f;
+              }
+            }
+          }
+#pragma unroll
+          for (int bb = 0; bb < 32; bb += 2) {
+            __nv_bfloat162 ph2 = __floats2bfloat162_rn(pe[bb], pe[bb + 1]);
+            pw[bb / 2] = *reinterpret_cast<uint32_t*>(&ph2);
+          }
+          if (warp == 0) FB_TRACE(0, g, 1);
+          mbar_wait(dp_done, ph);  // dP was issued behind [S | R]: it lands while P is being formed
+          tc_fence_after();
+          if (warp == 0) FB_TRACE(0, g, 2);
+          {
+            uint32_t dpv[32];
+            tmem_ld32(t_lane + FB_COL_DP + 32 * half, dpv);
+            tc_wait_ld();
+            tc_fence_before();
+            mbar_arrive(a1_done);  // S, R, dP are in registers: MMA 1 of the next step may overwrite them
+            const float nds = -Di * p.scale;
+#pragma unroll
+            for (int bb = 0; bb < 32; bb += 2) {
+              const float d0 = pe[bb] * fmaf(__uint_as_float(dpv[bb]), p.scale, nds);
+              const float d1 = pe[bb + 1] * fmaf(__uint_as_float(dpv[bb + 1]), p.scale, nds);
+              __nv_bfloat162 dh2 = __floats2bfloat162_rn(d0, d1);
+              dw[bb / 2] = *reinterpret_cast<uint32_t*>(&dh2);
+            }
+          }
+        }
+        if (warp == 0) FB_TRACE(0, g, 3);
+        // the previous item's dK / dV leave tensor memory before this item's first MMA 2 overwrites them
+        if (st == 0 && n > 0) {
+          mbar_wait(&m2_done[prev_last_g % NS], (prev_last_g / NS) & 1);
+          tc_fence_after();
+          write_dkv(prev);
+        }
+        // MMA 2 and the TMA store of step g-2 must have read this buffer of P / dS
+        if (g > 1) {
+          mbar_wait(&m2_done[(g - 2) % NS], ((g - 2) / NS) & 1);
+          mbar_wait(&ds_free[g & 1], ((g - 2) >> 1) & 1);
+        }
+        // P and dS rows: UMMA SWIZZLE_128B rows of 128 B (chunk kc of row a at position kc ^ (a & 7))
+        {
+          uint8_t* prow = sPdS + (g & 1) * FB_PDS_BYTES + a * 128;
+          uint8_t* drow = prow + 16384;
+#pragma unroll
+          for (int nn = 0; nn < 4; ++nn) {
+            const int pos = (((4 * half + nn) ^ (a & 7))) << 4;
+            *reinterpret_cast<uint4*>(prow + pos) = make_uint4(pw[4 * nn], pw[4 * nn + 1], pw[4 * nn + 2], pw[4 * nn + 3]);
+            *reinterpret_cast<uint4*>(drow + pos) = make_uint4(dw[4 * nn], dw[4 * nn + 1], dw[4 * nn + 2], dw[4 * nn + 3]);
+          }
+        }
+        if (warp == 0) FB_TRACE(0, g, 4);
+        fence_proxy_async_smem();
+        tc_fence_before();
+        mbar_arrive(&a_done[g & 1]);
+        if (warp == 0) FB_TRACE(0, g, 5);
+      }
+      prev = it;
+      prev_last_g = g - 1;
+    }
+    if (n > 0) {   // the last item
+      mbar_wait(&m2_done[prev_last_g % NS], (prev_last_g / NS) & 1);
+      tc_fence_after();
+      write_dkv(prev);
     }
   }
   tc_fence_before();
@@ -486,7 +565,7 @@ static int launch_bwd(const CUtensorMap& tq, const CUtensorMap& tk, const CUtens
     ME_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     configured = true;
   }
-  cudaEvent_t pe = prof_begin(3.0 * attn_unit_flops(static_cast<int>(grid.z), p.H, p.L, DH), st, 2);   // dP, dV, dK
+  cudaEvent_t pe = prof_begin(3.0 * attn_unit_flops(p.nb, p.H, p.L, DH), st, 2);   // dP, dV, dK
   kern<<<grid, FB_THREADS, smem, st>>>(tq, tk, tv, tdo, te, tds, p);
   prof_end(pe, st);
   ME_LAUNCH_CHECK();
@@ -603,7 +682,9 @@ int launch_attn_bwd_tc(const me_attn_bwd_args* ba) {
   for (int b0 = 0; b0 < B; b0 += slice) {
     const int nb = B - b0 < slice ? B - b0 : slice;
     p.b0 = b0;
-    dim3 grid((L + FB_BN - 1) / FB_BN, H, nb);
+    p.nb = nb;
+    const int n_items = ((L + FB_BN - 1) / FB_BN) * H * nb;
+    dim3 grid(n_items < sm_count() ? n_items : sm_count(), 1, 1);
     int rc;
     if (saved) {
       if (dh == 64) rc = launch_bwd<64, true>(tq, tps, tv, tdo, te, tds, p, grid, st);
