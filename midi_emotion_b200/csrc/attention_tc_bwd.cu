@@ -573,7 +573,8 @@ static int launch_bwd(const CUtensorMap& tq, const CUtensorMap& tk, const CUtens
 }
 
 int launch_attn_bwd_q_tc(const me_attn_bwd_args* ba, float* dE_ws, const CUtensorMap& tds, int tiles_per_head, int b0,
-                         int nb);
+                         int nb, int32_t* sched_dev);
+int64_t attn_bwd_q_sched_words(int L, int nb);
 
 // dS scratch: tiles of 128 query rows x 64 keys, per head nq * nkt + nq of them (enough for the causal and the
 // non-causal indexing)
@@ -644,6 +645,8 @@ int launch_attn_bwd_tc(const me_attn_bwd_args* ba) {
   // the dS scratch sits behind the private dE accumulators in the caller's workspace
   const int tph = static_cast<int>(ds_tiles_per_head(L));
   const int slice = ds_slice_batch(B, H, L);
+  const int64_t ds_floats = static_cast<int64_t>(slice) * H * tph * FB_BM * 64 / 2;
+  int32_t* sched_dev = reinterpret_cast<int32_t*>(ba->dq_acc + de_ws_floats(dh, a->max_seq) + ds_floats);
   CUtensorMap tds;
   {
     const uint64_t rows = static_cast<uint64_t>(slice) * H * tph * FB_BM;
@@ -696,7 +699,7 @@ int launch_attn_bwd_tc(const me_attn_bwd_args* ba) {
       else rc = launch_bwd<32, false>(tq, tk, tv, tdo, te, tds, p, grid, st);
     }
     if (rc) return rc;
-    if (launch_attn_bwd_q_tc(ba, ba->dq_acc, tds, tph, b0, nb)) return 1;
+    if (launch_attn_bwd_q_tc(ba, ba->dq_acc, tds, tph, b0, nb, sched_dev)) return 1;
   }
   {
     const int blocks = static_cast<int>((static_cast<int64_t>(a->max_seq) * (dh / 4) + 255) / 256);
@@ -718,7 +721,9 @@ extern "C" int me_debug_trace_set(long long* device_buf) {
 // of its bias-gradient column sums here -- 160 rows of at most 4 H dh columns -- which always fits.)
 extern "C" int64_t me_attention_backward_workspace_floats(int B, int H, int L, int dh, int max_seq) {
   const int64_t de = me::de_ws_floats(dh, max_seq);
-  const int64_t ds = static_cast<int64_t>(me::ds_slice_batch(B, H, L)) * H * me::ds_tiles_per_head(L) * me::FB_BM * 64 / 2;
+  const int nbs = me::ds_slice_batch(B, H, L);
+  const int64_t ds = static_cast<int64_t>(nbs) * H * me::ds_tiles_per_head(L) * me::FB_BM * 64 / 2 +
+                     me::attn_bwd_q_sched_words(L, nbs);   // + the query-side kernel's unit schedule (int32 words)
   const int64_t colsum = static_cast<int64_t>(160) * 4 * H * dh;
   return de + ds > colsum ? de + ds : colsum;
 }
