@@ -365,11 +365,14 @@ def train_leg(args, CFG, L, Ls, B, K, W, dev, rank, world, lib, with_e2e=True, c
 
     def forward_backward(tokens, cond, target):
         with torch.autocast("cuda", dtype=torch.bfloat16):
-            logits = model(tokens, cond)
-        if args.torch_loss:   # the reference's nn.CrossEntropyLoss (train.py:124,288-290) on the logits
+            if args.loss == "head":    # output head fused with the loss: no [M, V] logits (me_head_cross_entropy)
+                loss = model.loss(tokens, cond, target, ignore_index=0)
+            else:
+                logits = model(tokens, cond)
+        if args.loss == "torch":   # the reference's nn.CrossEntropyLoss (train.py:124,288-290) on the logits
             loss = torch.nn.functional.cross_entropy(logits.reshape(-1, logits.size(-1)).float(), target.reshape(-1),
                                                      ignore_index=0)
-        else:                 # the same loss, fused with its gradient and the top-k counts (me_cross_entropy)
+        elif args.loss == "fused":   # the same loss, fused with its gradient and the top-k counts (me_cross_entropy)
             loss = cross_entropy(logits, target, ignore_index=0)
         loss.backward()
         return loss
@@ -484,7 +487,9 @@ def main():
     ap.add_argument("--attn", default="auto", choices=["auto", "simt", "tensor"])
     ap.add_argument("--no-decode", action="store_true", help="skip the KV-cache decode measurement (configs[3])")
     ap.add_argument("--no-cfg3-leg", action="store_true", help="skip the short configs[2] leg (24L/1024d, seq 2048)")
-    ap.add_argument("--torch-loss", action="store_true", help="PyTorch cross-entropy instead of the fused kernel")
+    ap.add_argument("--loss", default="head", choices=["head", "fused", "torch"],
+                    help="head: output head fused with the cross-entropy (no logits tensor); fused: head GEMM + fused "
+                         "cross-entropy kernel; torch: head GEMM + torch.nn.functional.cross_entropy")
     ap.add_argument("--optim", default=DEFAULT_OPTIM, choices=["torch", "fused"],
                     help="torch: clip_grad_norm_ + torch.optim.Adam(fused=True); fused: ClipAdam (csrc/optimizer.cu)")
     args = ap.parse_args()
@@ -542,7 +547,7 @@ def main():
             "config": {"workload": "train step (fwd+CE+bwd+allreduce+clip+Adam) " + label,
                        "global_batch": world * B, "seq_len": Ls, "parallelism": f"dp{world}",
                        "l2": "per-step working set (activations > 10 GB) far exceeds the 126 MB L2; no flush needed",
-                       "attention": args.attn, "loss": "torch" if args.torch_loss else "fused", "optimizer": args.optim,
+                       "attention": args.attn, "loss": args.loss, "optimizer": args.optim,
                        "final_loss": r["final_loss"]},
             "e2e": {"value": e2e, "unit": "tokens/s", "h2d_bytes_per_step": r["h2d"], "d2h_bytes_per_step": 4,
                     "ms_per_step": ms_e2e / K},

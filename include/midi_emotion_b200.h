@@ -353,6 +353,21 @@ int me_cross_entropy(const void* logits, int dtype, int M, int V, int ld, const 
                      int64_t ignore_index, void* grad_logits, int ld_grad, float* stats, void* stream);
 
 /* ---------------------------------------------------------------------------------------
+ * Output head fused with the training loss (bf16, tcgen05): models/music_multi.py:106 (self.fc) + train.py:288-290
+ * (CrossEntropyLoss(ignore_index = pad)) + utils.py:15-80 (top-1 / top-5), without ever materialising the [M, V]
+ * logits: the vocabulary is swept twice per 128-row tile (log-sum-exp, then gradient).
+ *   x T=bf16 [M, K] (pitch ldx), W bf16 [V, K] (pitch ldw), bias f32 [V], targets int64 [M]
+ *   grad_logits bf16 [M, ld_grad] or NULL: d(mean loss)/d(logits), columns >= V zeroed -- what the head's backward
+ *               GEMMs read in place of the gradient me_cross_entropy would have written
+ *   stats f32 [4] out: { sum of per-row losses, number of counted rows, top-1 hits, top-5 hits }
+ * The logits are rounded to bf16 before the loss, exactly as the unfused path (and the reference under autocast)
+ * holds them.
+ * ------------------------------------------------------------------------------------- */
+int me_head_cross_entropy(const void* x, const void* W, const float* bias, int M, int V, int K, int ldx, int ldw,
+                          const int64_t* targets, int64_t ignore_index, void* grad_logits, int ld_grad, float* stats,
+                          void* stream);
+
+/* ---------------------------------------------------------------------------------------
  * Token pipeline of the training loader, data/loader.py:132-195 (Loader.__getitem__ after its random draws) with
  * data/data_processing.py:225-247 (transpose, tensor_to_ind_tensor), for a whole batch in one launch: transpose
  * the pitches of transposable events, map every (event, value) tuple to its token id, prepend the caller-built

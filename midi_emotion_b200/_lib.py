@@ -124,6 +124,8 @@ _PROTOS = {
     "me_colsum_ws": (C.c_int, [_vp, C.c_int, C.c_int, C.c_int, C.c_int, _vp, _vp, C.c_int64, _vp]),
     "me_convert_2d": (C.c_int, [_vp, C.c_int, C.c_int, _vp, C.c_int, C.c_int, C.c_int, C.c_int, _vp]),
     "me_convert_batched": (C.c_int, [_vp, C.c_int, _vp]),
+    "me_head_cross_entropy": (C.c_int, [_vp, _vp, _vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _vp, _i64, _vp, C.c_int,
+                                        _vp, _vp]),
     "me_token_pipeline": (C.c_int, [C.POINTER(TokenPipelineArgs)]),
     "me_sizeof_token_pipeline_args": (C.c_int, []),
     "me_pooled_head_forward": (C.c_int, [_vp, C.c_int, _vp, _vp, C.c_int, C.c_int, C.c_int, C.c_int, _vp, _vp]),

@@ -355,6 +355,47 @@ class _ModelFn(torch.autograd.Function):
         return (None, None, None, None, *grads)
 
 
+class _ModelLossFn(torch.autograd.Function):
+    """Whole model + training loss in one node: the output head is fused with the cross-entropy
+    (`me_head_cross_entropy`), so neither the [M, V] logits nor a separate gradient pass over them exist."""
+
+    @staticmethod
+    def forward(ctx, model, tokens, cond, target, ignore_index, need_grad, *params):
+        _, a = run_forward(model, tokens, cond, need_grad, head=False)
+        last = a.layers[-1]
+        V, d = model.vocab_size, model.embedding_dim
+        Vp = (V + 7) // 8 * 8
+        a.Vp = Vp
+        wc = model._weights(a.dtype)
+        tgt = target.reshape(-1).contiguous()
+        if tgt.numel() != a.M or tgt.dtype != torch.int64:
+            raise RuntimeError("midi_emotion_b200: target must be int64 with one entry per output position")
+        stats = torch.empty(4, device=tokens.device, dtype=torch.float32)
+        grad = torch.empty(a.M, Vp, device=tokens.device, dtype=torch.bfloat16) if need_grad else None
+        _lib.call("me_head_cross_entropy", ptr(last["out2_T"]), ptr(wc["Wfc"]), ptr(model.fc.bias), a.M, V, d, d, d,
+                  ptr(tgt), int(ignore_index), ptr(grad), Vp, ptr(stats), _stream())
+        ctx.model, ctx.tokens, ctx.cond, ctx.acts, ctx.grad = model, tokens, cond, a, grad
+        ctx.mark_non_differentiable(stats)
+        return stats[0] / stats[1], stats
+
+    @staticmethod
+    def backward(ctx, g_loss, _g_stats):
+        model, a, grad = ctx.model, ctx.acts, ctx.grad
+        if grad is None or a.layers is None or a.layers[0] is None or "z1" not in a.layers[0]:
+            raise RuntimeError("midi_emotion_b200: backward called twice or forward ran without grad")
+        grad.mul_(g_loss)      # d(mean loss)/d(logits) was written by the forward kernel; pad columns are zero
+        grads = run_backward(model, ctx.tokens, ctx.cond, a, grad, a.Vp)
+        ctx.acts = ctx.grad = None
+        return (None, None, None, None, None, None, *grads)
+
+
+def model_loss(model, tokens, cond, target, ignore_index=0):
+    """(mean cross-entropy over the non-ignored targets, stats[4] = {loss sum, count, top-1 hits, top-5 hits})."""
+    params = model._param_list()
+    need_grad = torch.is_grad_enabled() and any(p.requires_grad for p in params)
+    return _ModelLossFn.apply(model, tokens, cond, target, ignore_index, need_grad, *params)
+
+
 def model_apply(model, tokens, cond):
     params = model._param_list()
     need_grad = torch.is_grad_enabled() and any(p.requires_grad for p in params)

@@ -276,6 +276,30 @@ class MusicTransformer(nn.Module):
         from .autograd import model_apply
         return model_apply(self, x.contiguous(), condition)
 
+    def loss(self, x: torch.Tensor, condition: Optional[torch.Tensor], target: torch.Tensor, ignore_index: int = 0,
+             return_stats: bool = False):
+        """The training step's `output = model(input_, condition); loss = ce_loss(output_flat, target)` (train.py:283-290)
+        as ONE call: on the bf16 tensor-core path the output head is fused with the cross-entropy, so the
+        [batch, sequence, vocabulary] logits are never materialised.  Same value and gradients as
+        `cross_entropy(model(x, condition), target, ignore_index)`; `return_stats` adds the top-1 / top-5 counts of
+        utils.accuracy (train.py:256).  On the fp32 path it is exactly that composition."""
+        from .autograd import model_loss
+        from .loss import cross_entropy
+        if not x.is_cuda:
+            raise RuntimeError("midi_emotion_b200: CUDA tensors required (there is no CPU fallback)")
+        if self._resolve_dtype() != ME_BF16 or not self._vocab_head:
+            return cross_entropy(self(x, condition), target, ignore_index, return_stats)
+        if self.mode != 0:
+            if condition is None or condition.shape != (x.shape[0], 2):
+                raise RuntimeError("midi_emotion_b200: condition must be float [batch, 2]")
+            condition = condition.to(device=x.device, dtype=torch.float32).contiguous()
+        else:
+            condition = None
+        loss, stats = model_loss(self, x.contiguous(), condition, target, ignore_index)
+        if return_stats:
+            return loss, {"count": stats[1], "top1": stats[2], "top5": stats[3]}
+        return loss
+
     def extra_repr(self) -> str:
         return (f"d_model={self.embedding_dim}, d_inner={self.d_inner}, d_condition={self.d_condition}, "
                 f"layers={self.num_layer}, heads={self.num_head}, vocab={self.vocab_size}, "

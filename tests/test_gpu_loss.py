@@ -73,3 +73,70 @@ def test_training_step_with_fused_loss_matches_pytorch_loss(golden):
     for n, ref in grads[False][1].items():
         got = grads[True][1][n]
         assert (got - ref).abs().max().item() <= 2e-2 * max(ref.abs().max().item(), 1e-3 * top), n
+
+
+def test_fused_head_cross_entropy_kernel_against_ce_goldens(ce_golden):
+    """me_head_cross_entropy with an identity head (logits = x I^T + 0): loss, gradient and top-k counts of the
+    golden logits (rounded to bf16, as the head hands them over) without a logits tensor."""
+    from midi_emotion_b200 import _lib
+    from midi_emotion_b200._lib import ptr
+    g = ce_golden
+    t = g["target"].cuda().reshape(-1)
+    x32 = g["logits"].cuda().reshape(t.numel(), -1)
+    M, V = x32.shape
+    Kp = (V + 7) // 8 * 8
+    x = torch.zeros(M, Kp, device="cuda", dtype=torch.bfloat16)
+    x[:, :V] = x32.to(torch.bfloat16)
+    W = torch.zeros(V, Kp, device="cuda", dtype=torch.bfloat16)
+    W[:, :V] = torch.eye(V, device="cuda", dtype=torch.bfloat16)
+    bias = torch.zeros(V, device="cuda")
+    grad = torch.full((M, Kp), float("nan"), device="cuda", dtype=torch.bfloat16)
+    stats = torch.empty(4, device="cuda")
+    _lib.call("me_head_cross_entropy", ptr(x), ptr(W), ptr(bias), M, V, Kp, Kp, Kp, ptr(t), 0, ptr(grad), Kp, ptr(stats),
+              torch.cuda.current_stream().cuda_stream)
+    ref = x[:, :V].float().requires_grad_(True)
+    want = torch.nn.functional.cross_entropy(ref, t, ignore_index=0)
+    want.backward()
+    s = stats.cpu()
+    assert int(s[1]) == int((t != 0).sum())
+    assert abs(float(s[0] / s[1]) - want.item()) < 2e-5 * max(1.0, abs(want.item()))
+    assert torch.isfinite(grad.float()).all() and (grad[:, V:] == 0).all()
+    assert torch.allclose(grad[:, :V].float(), ref.grad, rtol=1e-2, atol=1e-7)
+    valid = t != 0
+    rank = (ref.detach()[valid] > ref.detach()[valid].gather(1, t[valid, None])).sum(-1)
+    assert int(s[2]) == int((rank < 1).sum()) and int(s[3]) == int((rank < 5).sum())
+
+
+def test_model_loss_fused_head_matches_unfused_composition(golden):
+    """model.loss(x, cond, target) == cross_entropy(model(x, cond), target): value, top-k counts and every gradient."""
+    g = golden
+    res = {}
+    for fused in (False, True):
+        model, _ = build_model(dict(g["cfg"]))
+        model.load_state_dict(g["params"])
+        model = model.cuda().train()
+        tok, cond, tgt = g["tokens"].cuda(), g["cond"].cuda(), g["target"].cuda()
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            if fused:
+                loss, stats = model.loss(tok, cond, tgt, ignore_index=0, return_stats=True)
+            else:
+                loss, stats = cross_entropy(model(tok, cond), tgt, ignore_index=0, return_stats=True)
+        (2.0 * loss).backward()
+        res[fused] = (loss.item(), {k: int(v.item()) for k, v in stats.items()},
+                      {n: p.grad.clone() for n, p in model.named_parameters()})
+    assert abs(res[True][0] - res[False][0]) < 1e-4 * max(1.0, abs(res[False][0]))
+    assert res[True][1] == res[False][1]
+    top = max(v.abs().max().item() for v in res[False][2].values())
+    for n, ref in res[False][2].items():
+        got = res[True][2][n]
+        assert (got - ref).abs().max().item() <= 2e-2 * max(ref.abs().max().item(), 1e-3 * top), n
+
+
+def test_model_loss_fp32_path_is_the_composition(golden):
+    g = golden
+    model, _ = build_model(dict(g["cfg"]))
+    model.load_state_dict(g["params"])
+    model = model.cuda().train()
+    model.precision = "fp32"
+    loss = model.loss(g["tokens"].cuda(), g["cond"].cuda(), g["target"].cuda())
+    assert abs(loss.item() - g["loss_fp32"]) < 2e-5
