@@ -203,7 +203,15 @@ def run_backward(model, tokens, cond, a: _Acts, g_logits: torch.Tensor, ld_g: Op
     if hook is not None:
         hook(flat_head)
     backward_stack(model, tokens, cond, a, d_x, grads)
-    return [grads[n] for n, _ in model.named_parameters()]
+    return [grads[n] for n in _param_names(model)]
+
+
+def _param_names(model):
+    names = model.__dict__.get("_param_names_cache")
+    if names is None:
+        names = [n for n, _ in model.named_parameters()]
+        model.__dict__["_param_names_cache"] = names
+    return names
 
 
 def _grouper(dev):

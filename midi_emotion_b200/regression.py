@@ -34,6 +34,8 @@ class MusicRegression(MusicTransformer):
         self.no_mask = bool(no_mask)
         # music_regression.py:65-68; default nn.Linear init (init_weights only touches the embedding, :71-73)
         self.fc = nn.Sequential(nn.Linear(embedding_dim, output_size), nn.Tanh())
+        self.__dict__.pop("_param_list_cache", None)   # (the head was replaced after the base constructor ran)
+        self.__dict__.pop("_param_names_cache", None)
         self._vocab_head = False
         self.causal = not self.no_mask       # no_mask=False would be generate_mask: causal + key pads
         self.use_keypad = not self.no_mask
@@ -87,4 +89,5 @@ class _RegressionFn(torch.autograd.Function):
             hook(flat)
         backward_stack(model, ctx.tokens, None, a, d_x, grads)
         ctx.acts = None
-        return (None, None, None, *[grads[n] for n, _ in model.named_parameters()])
+        from .autograd import _param_names
+        return (None, None, None, *[grads[n] for n in _param_names(model)])
