@@ -321,6 +321,8 @@ static int launch_fwd(const CUtensorMap& tq, const CUtensorMap& tk, const CUtens
   return 0;
 }
 
+int launch_attn_fwd2_tc(const me_attn_args* a);   // attention_tc_fwd2.cu: the pipelined one-CTA-per-SM schedule
+
 int launch_attn_fwd_tc(const me_attn_args* a) {
   ME_CHECK(me_device_is_sm100(), "me_attention_forward: the tensor-core path needs an sm_100 device");
   ME_CHECK(a->dtype == ME_BF16, "me_attention_forward: ME_ATTN_TENSOR computes in bf16 only");
@@ -331,6 +333,10 @@ int launch_attn_fwd_tc(const me_attn_args* a) {
   ME_CHECK(a->q_sh > 0 && a->q_si > 0 && a->q_sb > 0 && a->k_sh > 0 && a->v_sh > 0, "me_attention_forward: bad strides");
   ME_CHECK(a->o_si % 8 == 0 && a->o_sb % 8 == 0 && (reinterpret_cast<uintptr_t>(a->out) & 15) == 0,
            "me_attention_forward: output rows must be 16-byte aligned");
+  {
+    static const bool two_cta = [] { const char* e = getenv("ME_ATTN_FWD"); return e != nullptr && e[0] == '1'; }();
+    if (!two_cta) return launch_attn_fwd2_tc(a);
+  }
   CUtensorMap tq, tk, tv, te;
   if (qkv_map(&tq, a->q, a->dh, a->H, a->Lq, a->B, a->q_sh, a->q_si, a->q_sb, FA_BM)) return 1;
   if (qkv_map(&tk, a->k, a->dh, a->H, a->Lk, a->B, a->k_sh, a->k_sj, a->k_sb, FA_BN)) return 1;

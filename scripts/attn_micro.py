@@ -65,6 +65,22 @@ t_b = timeit(lambda: _lib.call("me_attention_backward", C.byref(ba)))
 print(f"attention B={B} H={H} L={L} dh={dh}: fwd {t_f * 1e3:.1f} us ({fwd_flops / t_f / 1e9:.1f} TFLOP/s useful), "
       f"bwd {t_b * 1e3:.1f} us ({2.5 * fwd_flops / t_b / 1e9:.1f} TFLOP/s useful, incl. prep/convert)")
 
+if os.environ.get("TRACE_FWD"):
+    # clock stamps of the heaviest CTA of the forward kernel (ME_TRACE=1 build)
+    buf = torch.zeros(4 * 20 * 8, dtype=torch.int64, device="cuda")
+    _lib.call("me_debug_trace_set", buf.data_ptr())
+    _lib.call("me_attention_forward", C.byref(a))
+    torch.cuda.synchronize()
+    _lib.call("me_debug_trace_set", None)
+    t = buf.cpu().view(4, 20, 8)
+    t0 = int(t[t > 0].min())
+    for role, name in enumerate(("teamA", "teamB", "mma  ", "cta  ")):
+        for st in range(20):
+            row = t[role, st]
+            if int(row.max()) == 0:
+                continue
+            print("fwd", name, "step", st, " ".join(f"{(int(v) - t0) if v > 0 else -1:7d}" for v in row[:8]))
+
 if os.environ.get("TRACE"):
     # clock stamps of one CTA of the query-side backward kernel (ME_TRACE=1 build, me_debug_trace_set)
     buf = torch.zeros(2 * 3 * 20 * 8, dtype=torch.int64, device="cuda")
@@ -82,4 +98,4 @@ if os.environ.get("TRACE"):
                 row = t[role, st]
                 if int(row.max()) == 0:
                     continue
-                print(kern, names[role], "step", st, " ".join(f"{(int(v) - t0) if v > 0 else -1:7d}" for v in row[:6]))
+                print(kern, names[role], "step", st, " ".join(f"{(int(v) - t0) if v > 0 else -1:7d}" for v in row[:8]))

@@ -392,6 +392,40 @@ def _run_attention_backward(impl, a, qkv, out, lse, dout, B, H, L, dh):
     return g_qkv, dE
 
 
+@pytest.mark.parametrize("L,dh", [(700, 64), (1024, 32)])
+def test_attention_tensor_core_forward_running_maximum_moves(L, dh):
+    """Keys whose logits grow along the sequence: the row maximum rises by far more than the 2^8 the forward
+    kernel's lazy running maximum tolerates, so its accumulator-rescale path (in TMEM) runs on most tiles."""
+    B, H, MS = 2, 2, 2048
+    g = torch.Generator(device="cuda").manual_seed(L + dh)
+    qkv = torch.randn(B, L, 3, H, dh, device="cuda", generator=g)
+    ramp = (1.0 + torch.arange(L, device="cuda").float() / 48.0).view(1, L, 1, 1)
+    qkv[:, :, 0] = qkv[:, :, 0].abs() * 0.9                   # q >= 0, k >= 0 and growing: logit ~ position
+    qkv[:, :, 1] = qkv[:, :, 1].abs() * ramp * 0.9
+    qkv = qkv.to(torch.bfloat16)
+    E = (torch.randn(MS, dh, device="cuda", generator=g) * 0.3).to(torch.bfloat16)
+    out, lse, a = _run_attention_forward(_lib.ATTN_TENSOR, qkv, E, None, B, H, L, dh, save_probs=True)
+    q = qkv[:, :, 0].permute(0, 2, 1, 3).float()
+    k = qkv[:, :, 1].permute(0, 2, 1, 3).float()
+    v = qkv[:, :, 2].permute(0, 2, 1, 3).float()
+    logits = (q @ k.transpose(-1, -2)) / dh ** 0.5
+    spread = (logits[..., -1, :].max(-1).values - logits[..., -1, :64].max(-1).values).min().item()
+    assert spread * 1.4427 > 3 * 8, spread                     # the case is what it claims to be
+    keypad = torch.zeros(B, L, device="cuda", dtype=torch.uint8)
+    want = _attn_reference(q, k, v, E.float(), keypad, MS).permute(0, 2, 1, 3).reshape(B, L, H * dh)
+    torch.cuda.synchronize()
+    assert torch.isfinite(out.float()).all() and torch.isfinite(lse).all()
+    assert rel_err(out.float(), want) < 8e-3, rel_err(out.float(), want)
+    out2, lse2, _ = _run_attention_forward(_lib.ATTN_SIMT, qkv, E, None, B, H, L, dh)
+    assert torch.allclose(lse, lse2, rtol=1e-3, atol=5e-3), (lse - lse2).abs().max()
+    # ... and the saved probability tiles (exponent offsets per tile) still drive a correct backward
+    dout = (torch.randn(B, L, H * dh, device="cuda", generator=g) * 0.5).to(torch.bfloat16)
+    g_tc, dE_tc = _run_attention_backward(_lib.ATTN_TENSOR, a, qkv, out, lse, dout, B, H, L, dh)
+    g_si, dE_si = _run_attention_backward(_lib.ATTN_SIMT, a, qkv, out, lse, dout, B, H, L, dh)
+    assert rel_err(g_tc.float(), g_si.float()) < 2e-2, rel_err(g_tc.float(), g_si.float())
+    assert rel_err(dE_tc, dE_si) < 2e-2, rel_err(dE_tc, dE_si)
+
+
 @pytest.mark.parametrize("B,H,L,dh", [(2, 2, 37, 48), (1, 3, 130, 64), (2, 1, 64, 32), (2, 2, 300, 64),
                                       (1, 2, 1024, 64), (1, 1, 2048, 64), (2, 4, 1026, 48)])
 @pytest.mark.parametrize("pad", [False, True])
