@@ -255,6 +255,14 @@ typedef struct me_layer_args {
   /* optional saved attention probabilities (me_attn_args.p_tiles / m_tiles), ME_ATTN_TENSOR training only */
   void* attn_p;
   float* attn_m;
+  /* Optional (ME_BF16 with saved statistics): the layer input handed over as the PREVIOUS LayerNorm's saved state
+   * instead of its fp32 output: with xin_mean != NULL, x_f32 is that LayerNorm's pre-normalisation sum z and the
+   * residual input is x = (z - xin_mean) * xin_rstd * xin_gamma + xin_beta, recomputed on the fly with the very
+   * expression that LayerNorm evaluates -- the fp32 copy of a LayerNorm output (music_multi.py:129,134; read exactly
+   * once, by the next LayerNorm) then never travels through HBM.  out1_f32 may be NULL when z1 / mean1 / rstd1 are
+   * given (LN2 re-derives out1 the same way), out2_f32 may be NULL when the caller chains z2 / mean2 / rstd2 into
+   * the next layer's xin_*.  All NULL: x_f32 is the input itself and both fp32 outputs are written. */
+  const float *xin_mean, *xin_rstd, *xin_gamma, *xin_beta;
 } me_layer_args;
 int me_layer_forward(const me_layer_args* a);
 

@@ -41,7 +41,8 @@ class AttnBwdArgs(C.Structure):
 
 _LAYER_PTRS = ["x_f32", "x_T", "keypad", "Wqkv", "bqkv", "E", "Wo", "bo", "ln1_w", "ln1_b", "W1", "b1", "W2", "b2",
                "ln2_w", "ln2_b", "qkv", "attn_o", "lse", "proj", "z1", "mean1", "rstd1", "out1_f32", "out1_T", "h",
-               "z2", "mean2", "rstd2", "out2_f32", "out2_T", "stream", "attn_p", "attn_m"]
+               "z2", "mean2", "rstd2", "out2_f32", "out2_T", "stream", "attn_p", "attn_m", "xin_mean", "xin_rstd",
+               "xin_gamma", "xin_beta"]
 
 
 class ConvertDesc(C.Structure):

@@ -46,7 +46,7 @@ def _layer_args(model, wl: dict, lay, act: dict, x_f32, x_T, keypad, a: _Acts, l
     la.W1, la.b1, la.W2, la.b2 = ptr(wl["W1"]), ptr(lay.FFN_pre.bias), ptr(wl["W2"]), ptr(lay.FFN_suf.bias)
     la.ln2_w, la.ln2_b = ptr(lay.layernorm2.weight), ptr(lay.layernorm2.bias)
     for k in ("qkv", "attn_o", "lse", "proj", "z1", "mean1", "rstd1", "out1_f32", "out1_T", "h", "z2", "mean2",
-              "rstd2", "out2_f32", "out2_T", "attn_p", "attn_m"):
+              "rstd2", "out2_f32", "out2_T", "attn_p", "attn_m", "xin_mean", "xin_rstd", "xin_gamma", "xin_beta"):
         setattr(la, k, ptr(act.get(k)))
     la.stream = _stream()
     return la
@@ -111,11 +111,18 @@ def run_forward(model, tokens: torch.Tensor, cond: Optional[torch.Tensor], need_
             scratch = act
         else:
             act = dict(scratch)  # inference: reuse the big buffers layer after layer
-        act["out1_f32"] = torch.empty(M, d, **f32)
+        # Training in bf16: the fp32 copy of a LayerNorm output is read exactly once, by the next LayerNorm -- it is
+        # not written at all, the next LayerNorm re-derives it from the saved z / mean / rstd (me_layer_args.xin_*).
+        lazy = need_grad and dtype != ME_F32
+        act["out1_f32"] = None if lazy else torch.empty(M, d, **f32)
         act["out1_T"] = act["out1_f32"] if dtype == ME_F32 else torch.empty(M, d, **tt)
-        act["out2_f32"] = torch.empty(M, d, **f32)
+        act["out2_f32"] = None if lazy else torch.empty(M, d, **f32)
         act["out2_T"] = act["out2_f32"] if dtype == ME_F32 else torch.empty(M, d, **tt)
         act["x_f32"], act["x_T"] = x_f32, x_T
+        if lazy and l > 0:
+            prev, prev_lay = a.layers[-1], model.enc_layers[l - 1]
+            act.update(xin_mean=prev["mean2"], xin_rstd=prev["rstd2"], xin_gamma=prev_lay.layernorm2.weight,
+                       xin_beta=prev_lay.layernorm2.bias)
         la = _layer_args(model, wc["layers"][l], lay, act, x_f32, x_T, keypad, a, l)
         if need_grad:
             la.training = 1  # keep the statistics needed by backward even when dropout is off
@@ -123,7 +130,7 @@ def run_forward(model, tokens: torch.Tensor, cond: Optional[torch.Tensor], need_
         _lib.call("me_layer_forward", C.byref(la))
         if kv_sink is not None:
             kv_sink(l, act["qkv"])
-        x_f32, x_T = act["out2_f32"], act["out2_T"]
+        x_f32, x_T = (act["z2"] if lazy else act["out2_f32"]), act["out2_T"]
         if need_grad:
             act.pop("proj", None)
             a.layers.append(act)

@@ -183,12 +183,20 @@ template <> struct Vec4<bf16> {
   }
 };
 
+// The normalisation itself; one definition so that a deferred output re-derived by the next LayerNorm has the bits
+// the producing LayerNorm would have written (explicit fma: no contraction choice left to the compiler).
+__device__ __forceinline__ float ln_apply(float z, float mean, float rstd, float g, float b) {
+  return __fmaf_rn(__fmul_rn(__fsub_rn(z, mean), rstd), g, b);
+}
+
 template <typename T, int NCH>
 __global__ void __launch_bounds__(LN_THREADS)
 add_ln_fwd_kernel(const float* __restrict__ x_res, const T* __restrict__ y, const float* __restrict__ gamma,
                   const float* __restrict__ beta, float eps, int M, int d, float p, uint64_t seed,
                   float* __restrict__ out_f32, T* __restrict__ out_T, float* __restrict__ zsave,
-                  float* __restrict__ mean_out, float* __restrict__ rstd_out) {
+                  float* __restrict__ mean_out, float* __restrict__ rstd_out, const float* __restrict__ src_mean,
+                  const float* __restrict__ src_rstd, const float* __restrict__ src_gamma,
+                  const float* __restrict__ src_beta) {
   const int lane = threadIdx.x & 31;
   const int wpb = LN_THREADS / 32;
   const int64_t warp0 = static_cast<int64_t>(blockIdx.x) * wpb + (threadIdx.x >> 5);
@@ -197,10 +205,17 @@ add_ln_fwd_kernel(const float* __restrict__ x_res, const T* __restrict__ y, cons
   const uint32_t seed32 = dropout_seed32(seed);
   const float inv_d = 1.f / static_cast<float>(d);
   const bool alias = static_cast<const void*>(out_T) == static_cast<const void*>(out_f32);
-  extern __shared__ float ln_smem[];  // gamma | beta: keeps 2*d floats out of every thread's registers
+  extern __shared__ float ln_smem[];  // gamma | beta (| source gamma | beta): keeps them out of every thread's registers
+  // src_mean != NULL: x_res holds the pre-normalisation sums of the LayerNorm that produced the residual input, and
+  // the input is re-derived here (me_layer_args.xin_*) with that LayerNorm's own expression, ln_apply()
+  const bool lazy = src_mean != nullptr;
   for (int c = threadIdx.x; c < d; c += LN_THREADS) {
     ln_smem[c] = gamma[c];
     ln_smem[d + c] = beta[c];
+    if (lazy) {
+      ln_smem[2 * d + c] = src_gamma[c];
+      ln_smem[3 * d + c] = src_beta[c];
+    }
   }
   __syncthreads();
   for (int64_t row = warp0; row < M; row += nwarps) {
@@ -215,6 +230,18 @@ add_ln_fwd_kernel(const float* __restrict__ x_res, const T* __restrict__ y, cons
       const int64_t idx = row * d + (c < d ? c : 0);
       Vec4<T>::load(y + idx, yv[k]);
       Vec4<float>::load(x_res + idx, z[k]);
+    }
+    if (lazy) {
+      const float smu = src_mean[row], srs = src_rstd[row];
+#pragma unroll
+      for (int k = 0; k < NCH; ++k) {
+        const int c = 4 * (lane + 32 * k);
+        float gm[4], bt[4];
+        Vec4<float>::load(ln_smem + 2 * d + (c < d ? c : 0), gm);
+        Vec4<float>::load(ln_smem + 3 * d + (c < d ? c : 0), bt);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) z[k][e] = ln_apply(z[k][e], smu, srs, gm[e], bt[e]);
+      }
     }
 #pragma unroll
     for (int k = 0; k < NCH; ++k) {
@@ -254,9 +281,9 @@ add_ln_fwd_kernel(const float* __restrict__ x_res, const T* __restrict__ y, cons
         Vec4<float>::load(ln_smem + c, gm);
         Vec4<float>::load(ln_smem + d + c, bt);
 #pragma unroll
-        for (int e = 0; e < 4; ++e) o[e] = (z[k][e] - mean) * rstd * gm[e] + bt[e];
+        for (int e = 0; e < 4; ++e) o[e] = ln_apply(z[k][e], mean, rstd, gm[e], bt[e]);
         if (zsave) Vec4<float>::store(zsave + idx, z[k]);
-        Vec4<float>::store(out_f32 + idx, o);
+        if (out_f32) Vec4<float>::store(out_f32 + idx, o);
         if (out_T != nullptr && !alias) Vec4<T>::store(out_T + idx, o);
       }
     }
@@ -489,10 +516,11 @@ int launch_embed(const int64_t* tokens, const float* cond, const float* emb_w, c
 template <typename T>
 static int ln_fwd_dispatch(int nch, int blocks, cudaStream_t st, const float* x_res, const T* y, const float* gamma,
                            const float* beta, float eps, int M, int d, float p, uint64_t seed, float* out_f32,
-                           T* out_T, float* z, float* mean, float* rstd) {
+                           T* out_T, float* z, float* mean, float* rstd, const float* src_mean,
+                           const float* src_rstd, const float* src_gamma, const float* src_beta) {
 #define ME_LN_FWD(N)                                                                                        \
-  add_ln_fwd_kernel<T, N><<<blocks, LN_THREADS, 2 * d * sizeof(float), st>>>(x_res, y, gamma, beta, eps, M, d, p, \
-                                                                             seed, out_f32, out_T, z, mean, rstd)
+  add_ln_fwd_kernel<T, N><<<blocks, LN_THREADS, (src_mean ? 4 : 2) * d * sizeof(float), st>>>(               \
+      x_res, y, gamma, beta, eps, M, d, p, seed, out_f32, out_T, z, mean, rstd, src_mean, src_rstd, src_gamma, src_beta)
   switch (nch) {
     case 1: ME_LN_FWD(1); break;
     case 2: ME_LN_FWD(2); break;
@@ -515,18 +543,21 @@ static int ln_nch(int d) {
 
 int launch_add_ln_fwd(const float* x_res, const void* y, int dtype, const float* gamma, const float* beta,
                       float eps, int M, int d, float p, uint64_t seed, float* out_f32, void* out_T, float* z,
-                      float* mean, float* rstd, cudaStream_t st) {
+                      float* mean, float* rstd, const float* src_mean, const float* src_rstd, const float* src_gamma,
+                      const float* src_beta, cudaStream_t st) {
   ME_CHECK(d % 4 == 0 && d <= 1024, "layernorm: d=%d must be a multiple of 4 and <= 1024", d);
+  ME_CHECK(out_f32 != nullptr || (out_T != nullptr && dtype == ME_BF16), "layernorm: no output");
   const int wpb = LN_THREADS / 32;
   int blocks = (M + wpb - 1) / wpb;
   const int cap = sm_count() * 8;
   if (blocks > cap) blocks = cap;
   if (dtype == ME_BF16)
     ln_fwd_dispatch<bf16>(ln_nch(d), blocks, st, x_res, static_cast<const bf16*>(y), gamma, beta, eps, M, d, p, seed,
-                          out_f32, static_cast<bf16*>(out_T), z, mean, rstd);
+                          out_f32, static_cast<bf16*>(out_T), z, mean, rstd, src_mean, src_rstd, src_gamma, src_beta);
   else
     ln_fwd_dispatch<float>(ln_nch(d), blocks, st, x_res, static_cast<const float*>(y), gamma, beta, eps, M, d, p,
-                           seed, out_f32, static_cast<float*>(out_T), z, mean, rstd);
+                           seed, out_f32, static_cast<float*>(out_T), z, mean, rstd, src_mean, src_rstd, src_gamma,
+                           src_beta);
   ME_LAUNCH_CHECK();
   return 0;
 }
@@ -732,7 +763,7 @@ extern "C" int me_add_layernorm_forward(const float* x_res, const void* y, int d
                                         float* rstd, void* stream) {
   ME_CHECK(M > 0 && d > 0 && d <= 1024, "me_add_layernorm_forward: bad dims M=%d d=%d", M, d);
   return launch_add_ln_fwd(x_res, y, dtype, gamma, beta, eps, M, d, dropout_p, seed, out_f32, out_T, z, mean,
-                           rstd, static_cast<cudaStream_t>(stream));
+                           rstd, nullptr, nullptr, nullptr, nullptr, static_cast<cudaStream_t>(stream));
 }
 
 extern "C" int me_add_layernorm_backward(const float* dout, const float* dout_add, const float* z,

@@ -13,7 +13,8 @@ int launch_gemm_f32(const float* A, const float* B, float* D, int M, int N, int 
                     const float* relu_mask, int ldmask, cudaStream_t st);
 int launch_add_ln_fwd(const float* x_res, const void* y, int dtype, const float* gamma, const float* beta,
                       float eps, int M, int d, float p, uint64_t seed, float* out_f32, void* out_T, float* z,
-                      float* mean, float* rstd, cudaStream_t st);
+                      float* mean, float* rstd, const float* src_mean, const float* src_rstd, const float* src_gamma,
+                      const float* src_beta, cudaStream_t st);
 int launch_add_ln_bwd(const float* dout, const float* dout_add, const void* dout_add_T, const float* z,
                       const float* mean, const float* rstd, const float* gamma, int M, int d, float p, uint64_t seed,
                       int dtype, float* dz_f32, void* dy_T, float* d_gamma, float* d_beta, float* d_ybias,
@@ -52,8 +53,12 @@ static int check_layer(const me_layer_args* a, const char* who) {
   ME_CHECK(a->x_f32 && a->x_T && a->Wqkv && a->bqkv && a->E && a->Wo && a->bo && a->W1 && a->b1 && a->W2 && a->b2 &&
                a->ln1_w && a->ln1_b && a->ln2_w && a->ln2_b,
            "%s: NULL input or weight pointer", who);
-  ME_CHECK(a->qkv && a->attn_o && a->proj && a->out1_f32 && a->out1_T && a->h && a->out2_f32 && a->out2_T,
-           "%s: NULL activation pointer", who);
+  ME_CHECK(a->qkv && a->attn_o && a->proj && a->out1_T && a->h && a->out2_T, "%s: NULL activation pointer", who);
+  ME_CHECK(a->out1_f32 || (a->z1 && a->mean1 && a->rstd1), "%s: out1_f32 may only be NULL when z1/mean1/rstd1 are saved", who);
+  ME_CHECK(a->out2_f32 || (a->z2 && a->mean2 && a->rstd2), "%s: out2_f32 may only be NULL when z2/mean2/rstd2 are saved", who);
+  ME_CHECK(a->xin_mean == nullptr || (a->xin_rstd && a->xin_gamma && a->xin_beta), "%s: incomplete xin_* state", who);
+  ME_CHECK((a->xin_mean == nullptr && a->out1_f32 && a->out2_f32) || a->dtype == ME_BF16,
+           "%s: the deferred LayerNorm outputs are a ME_BF16 option", who);
   return 0;
 }
 
@@ -90,15 +95,18 @@ static int layer_tail(const me_layer_args* a, int M, cudaStream_t st) {
   if (linear(dt, a->attn_o, a->Wo, a->proj, M, d, d, d, d, d, 0, 0, false, ME_EPI_BIAS, a->bo, nullptr, nullptr, 0, st))
     return 1;
   if (launch_add_ln_fwd(a->x_f32, a->proj, dt, a->ln1_w, a->ln1_b, a->ln_eps, M, d, p, s1, a->out1_f32, a->out1_T,
-                        a->z1, a->mean1, a->rstd1, st))
+                        a->z1, a->mean1, a->rstd1, a->xin_mean, a->xin_rstd, a->xin_gamma, a->xin_beta, st))
     return 1;
   if (linear(dt, a->out1_T, a->W1, a->h, M, di, d, d, d, di, 0, 0, false, ME_EPI_BIAS | ME_EPI_RELU, a->b1, nullptr,
              nullptr, 0, st))
     return 1;
   if (linear(dt, a->h, a->W2, a->proj, M, d, di, di, di, d, 0, 0, false, ME_EPI_BIAS, a->b2, nullptr, nullptr, 0, st))
     return 1;
-  if (launch_add_ln_fwd(a->out1_f32, a->proj, dt, a->ln2_w, a->ln2_b, a->ln_eps, M, d, p, s2, a->out2_f32, a->out2_T,
-                        a->z2, a->mean2, a->rstd2, st))
+  // (out1 not materialised in fp32: LN2 re-derives it from LN1's saved state)
+  const bool lazy1 = a->out1_f32 == nullptr;
+  if (launch_add_ln_fwd(lazy1 ? a->z1 : a->out1_f32, a->proj, dt, a->ln2_w, a->ln2_b, a->ln_eps, M, d, p, s2,
+                        a->out2_f32, a->out2_T, a->z2, a->mean2, a->rstd2, lazy1 ? a->mean1 : nullptr,
+                        lazy1 ? a->rstd1 : nullptr, lazy1 ? a->ln1_w : nullptr, lazy1 ? a->ln1_b : nullptr, st))
     return 1;
   return 0;
 }
