@@ -145,7 +145,7 @@ def test_gradients_cfg2_against_live_oracle():
             e = rel_err(p.grad.cpu(), ref)
             if e > worst:
                 worst, worst_name = e, n
-        res[precision] = {"loss": float(loss), "oracle_loss": float(want_loss), "worst_grad_rel_err": worst,
+        res[precision] = {"loss": float(loss.detach()), "oracle_loss": float(want_loss), "worst_grad_rel_err": worst,
                           "worst_grad": worst_name}
     model.precision = "auto"
     RESULTS["cfg2_gradients_B1"] = res
