@@ -200,6 +200,224 @@ attn_decode_kernel(const bf16* __restrict__ q, const bf16* __restrict__ k, const
   }
 }
 
+// ------------------------------------------------------------------------------------------------------
+// Streaming variant for contiguous cache rows (k_sj == v_sj == dh: the [B, H, T_max, dh] KV cache): the K, V and E
+// rows of 64 keys are brought in by bulk copies (cp.async.bulk, one elected thread, mbarrier completion) into a
+// four-stage shared-memory ring, so that 128 KB per SM are in flight without costing a register -- the register
+// double buffer of the kernel above holds 65 KB per SM, 1.5x the bandwidth-latency product, and stops at
+// 5.05 TB/s.  Same thread layout and arithmetic: four lanes per key, every 4-lane group its own running state.
+// ------------------------------------------------------------------------------------------------------
+constexpr int ADS_KEYS = 64;      // keys per stage
+constexpr int ADS_STAGES = 4;
+
+__device__ __forceinline__ void bulk_load_1d(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+
+template <int DHP, int DH>
+__global__ void __launch_bounds__(AD_WARPS * 32 + 32, 2)
+attn_decode_stream_kernel(const bf16* __restrict__ q, const bf16* __restrict__ k, const bf16* __restrict__ v,
+                          const bf16* __restrict__ E, bf16* __restrict__ out, AdParams p, int n_items) {
+  constexpr int NC = DHP / 32;       // chunks per lane
+  constexpr int ND = NC * 8;         // dims per lane
+  constexpr int ROW = DH * 2;        // bytes per cache row
+  constexpr int TILE = ADS_KEYS * ROW;
+  extern __shared__ __align__(128) uint8_t ads_smem[];
+  // per stage: K | V | E tiles of 64 rows
+  uint64_t* full = reinterpret_cast<uint64_t*>(ads_smem + ADS_STAGES * 3 * TILE);
+  uint64_t* empty = full + ADS_STAGES;
+  float (*red)[DHP + 2] = reinterpret_cast<float (*)[DHP + 2]>(empty + ADS_STAGES);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int g = lane & 3, kslot = lane >> 2;
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < ADS_STAGES; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], AD_WARPS);
+    }
+    fence_mbar_init();
+  }
+  pdl_launch_dependents();
+  __syncthreads();
+  pdl_wait();
+  const int t = p.pos_dev ? *p.pos_dev : p.q_pos0;
+  const int nkeys = t + 1, nchunks = (nkeys + ADS_KEYS - 1) / ADS_KEYS;
+  const bf16* Eb = E + static_cast<int64_t>(p.max_seq - 1 - t) * DH;  // row for key j is Eb + j*DH
+  // Persistent: CTA c walks the (batch, head) items c, c + grid, ...; the chunks of all its items form one stream
+  // G = 0, 1, ... (stage G % STAGES), so the loads of the next item are in flight while this one is merged.
+  const int my_items = (n_items - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) / static_cast<int>(gridDim.x);
+  const int total = my_items * nchunks;
+
+  auto issue = [&](int G) {   // (thread 0) chunk G of the stream -> stage G % STAGES
+    const int s = G % ADS_STAGES;
+    const int item = blockIdx.x + (G / nchunks) * gridDim.x, c = G % nchunks;
+    const int b = item / p.H, h = item - b * p.H;
+    const int rows = min(ADS_KEYS, nkeys - c * ADS_KEYS);
+    const uint32_t bytes = static_cast<uint32_t>(rows) * ROW;
+    uint8_t* st = ads_smem + s * 3 * TILE;
+    mbar_arrive_expect_tx(&full[s], 3 * bytes);
+    const int64_t off = static_cast<int64_t>(c) * ADS_KEYS * DH;
+    bulk_load_1d(st, k + b * p.k_sb + h * p.k_sh + off, bytes, &full[s]);
+    bulk_load_1d(st + TILE, v + b * p.v_sb + h * p.v_sh + off, bytes, &full[s]);
+    bulk_load_1d(st + 2 * TILE, Eb + off, bytes, &full[s]);
+  };
+  if (warp == AD_WARPS) {   // producer warp: keeps the ring full, never in the way of the compute warps
+    if (lane == 0) {
+      for (int G = 0; G < total; ++G) {
+        if (G >= ADS_STAGES) mbar_wait(&empty[G % ADS_STAGES], ((G / ADS_STAGES) - 1) & 1);
+        issue(G);
+      }
+    }
+    return;
+  }
+
+  bool live[NC];
+#pragma unroll
+  for (int c = 0; c < NC; ++c) live[c] = 8 * (g + 4 * c) < DH;
+
+  int G = 0;
+  for (int it = 0; it < my_items; ++it) {
+    const int item = blockIdx.x + it * gridDim.x;
+    const int b = item / p.H, h = item - b * p.H;
+    const uint8_t* kp = p.keypad ? p.keypad + b * p.keypad_ld : nullptr;
+    float qf[ND];
+    {
+      const bf16* qrow = q + b * p.q_sb + h * p.q_sh;
+#pragma unroll
+      for (int c = 0; c < NC; ++c) {
+        uint4 u = make_uint4(0, 0, 0, 0);
+        if (live[c]) u = __ldg(reinterpret_cast<const uint4*>(qrow) + g + 4 * c);
+        const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          qf[c * 8 + 2 * e] = bf_lo(w[e]) * p.scale_log2;
+          qf[c * 8 + 2 * e + 1] = bf_hi(w[e]) * p.scale_log2;
+        }
+      }
+    }
+    float m = -INFINITY, l = 0.f;
+    float o[ND];
+#pragma unroll
+    for (int c = 0; c < ND; ++c) o[c] = 0.f;
+
+    for (int c = 0; c < nchunks; ++c, ++G) {
+      const int s = G % ADS_STAGES;
+      const uint8_t* st = ads_smem + s * 3 * TILE;
+      const int jr = warp * 8 + kslot;               // row of this lane group inside the chunk
+      const int j = c * ADS_KEYS + jr;
+      uint32_t pad = 1u;
+      if (j <= t) pad = kp ? static_cast<uint32_t>(__ldg(kp + j)) : 0u;
+      mbar_wait(&full[s], (G / ADS_STAGES) & 1);
+      {
+        // (every lane goes through the shuffles; the lanes past the last key carry zeros and pad = 1)
+        uint4 kr[NC], er[NC], vr[NC];
+#pragma unroll
+        for (int cc = 0; cc < NC; ++cc) {
+          kr[cc] = er[cc] = vr[cc] = make_uint4(0, 0, 0, 0);
+          if (live[cc] && j <= t) {
+            const int off = jr * ROW + (g + 4 * cc) * 16;
+            kr[cc] = *reinterpret_cast<const uint4*>(st + off);
+            er[cc] = *reinterpret_cast<const uint4*>(st + 2 * TILE + off);
+            vr[cc] = *reinterpret_cast<const uint4*>(st + TILE + off);
+          }
+        }
+        float x = dot_chunks<NC>(qf, kr) + dot_chunks<NC>(qf, er);
+        x += __shfl_xor_sync(0xffffffffu, x, 1);
+        x += __shfl_xor_sync(0xffffffffu, x, 2);
+        if (pad == 0u) {
+          if (x > m) {
+            const float a = fast_exp2(m - x);
+            l *= a;
+#pragma unroll
+            for (int cc = 0; cc < ND; ++cc) o[cc] *= a;
+            m = x;
+          }
+          const float pj = fast_exp2(x - m);
+          l += pj;
+#pragma unroll
+          for (int cc = 0; cc < NC; ++cc) {
+            const uint32_t w[4] = {vr[cc].x, vr[cc].y, vr[cc].z, vr[cc].w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              o[cc * 8 + 2 * e] = fmaf(pj, bf_lo(w[e]), o[cc * 8 + 2 * e]);
+              o[cc * 8 + 2 * e + 1] = fmaf(pj, bf_hi(w[e]), o[cc * 8 + 2 * e + 1]);
+            }
+          }
+        }
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&empty[s]);
+    }
+
+    // merge the 8 key slots of the warp (lanes with equal g), then the warps of the block
+    float wm = m;
+#pragma unroll
+    for (int sft = 4; sft <= 16; sft <<= 1) wm = fmaxf(wm, __shfl_xor_sync(0xffffffffu, wm, sft));
+    const float sc = (m == -INFINITY) ? 0.f : fast_exp2(m - wm);
+    l *= sc;
+#pragma unroll
+    for (int c = 0; c < ND; ++c) o[c] *= sc;
+#pragma unroll
+    for (int sft = 4; sft <= 16; sft <<= 1) {
+      l += __shfl_xor_sync(0xffffffffu, l, sft);
+#pragma unroll
+      for (int c = 0; c < ND; ++c) o[c] += __shfl_xor_sync(0xffffffffu, o[c], sft);
+    }
+    if (kslot == 0) {
+      if (g == 0) {
+        red[warp][DHP] = wm;
+        red[warp][DHP + 1] = l;
+      }
+#pragma unroll
+      for (int c = 0; c < NC; ++c)
+#pragma unroll
+        for (int e = 0; e < 8; ++e) red[warp][8 * (g + 4 * c) + e] = o[c * 8 + e];
+    }
+    named_bar_sync(1, AD_WARPS * 32);
+    if (warp == 0) {
+      float gm = -INFINITY;
+#pragma unroll
+      for (int w = 0; w < AD_WARPS; ++w) gm = fmaxf(gm, red[w][DHP]);
+      float gl = 0.f;
+      float acc[DHP / 32];
+#pragma unroll
+      for (int c = 0; c < DHP / 32; ++c) acc[c] = 0.f;
+#pragma unroll
+      for (int w = 0; w < AD_WARPS; ++w) {
+        const float wmx = red[w][DHP];
+        const float s2 = (wmx == -INFINITY) ? 0.f : fast_exp2(wmx - gm);
+        gl += red[w][DHP + 1] * s2;
+#pragma unroll
+        for (int c = 0; c < DHP / 32; ++c) acc[c] += red[w][lane + 32 * c] * s2;
+      }
+      const float inv = gl > 0.f ? 1.f / gl : 0.f;  // fully masked row -> 0
+      bf16* orow = out + b * p.o_sb + h * DH;
+#pragma unroll
+      for (int c = 0; c < DHP / 32; ++c)
+        if (lane + 32 * c < DH) orow[lane + 32 * c] = __float2bfloat16_rn(acc[c] * inv);
+    }
+    named_bar_sync(1, AD_WARPS * 32);   // `red` is free again
+  }
+}
+
+template <int DHP, int DH>
+static int launch_decode_stream(const bf16* q, const bf16* k, const bf16* v, const bf16* E, bf16* out, const AdParams& p,
+                                int n_items, cudaStream_t st) {
+  constexpr int SMEM = ADS_STAGES * 3 * ADS_KEYS * DH * 2 + 2 * ADS_STAGES * 8 + AD_WARPS * (DHP + 2) * 4;
+  auto kern = attn_decode_stream_kernel<DHP, DH>;
+  static bool configured = false;
+  if (!configured) {
+    ME_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
+    configured = true;
+  }
+  const int grid = std::min(n_items, 2 * sm_count());
+  ME_CUDA(launch_pdl(kern, dim3(grid), dim3(AD_WARPS * 32 + 32), SMEM, st, q, k, v, E, out, p, n_items));
+  ME_LAUNCH_CHECK();
+  return 0;
+}
+
 int launch_attn_decode(const me_attn_args* a) {
   AdParams p;
   p.H = a->H; p.max_seq = a->max_seq; p.q_pos0 = a->q_pos0;
@@ -216,6 +434,16 @@ int launch_attn_decode(const me_attn_args* a) {
   const bf16* v = static_cast<const bf16*>(a->v);
   const bf16* E = static_cast<const bf16*>(a->E);
   bf16* out = static_cast<bf16*>(a->out);
+  // contiguous cache rows, 16-byte aligned bases: the bulk-copy pipeline (ME_ATTN_DECODE=1 keeps the register one)
+  static const bool reg_pipe = [] { const char* e = getenv("ME_ATTN_DECODE"); return e != nullptr && e[0] == '1'; }();
+  const bool contiguous = a->k_sj == a->dh && a->v_sj == a->dh && a->k_sh % 8 == 0 && a->k_sb % 8 == 0 &&
+                          a->v_sh % 8 == 0 && a->v_sb % 8 == 0 && (reinterpret_cast<uintptr_t>(a->k) & 15) == 0 &&
+                          (reinterpret_cast<uintptr_t>(a->v) & 15) == 0 && (reinterpret_cast<uintptr_t>(a->E) & 15) == 0;
+  if (contiguous && !reg_pipe) {
+    if (a->dh == 64) return launch_decode_stream<64, 64>(q, k, v, E, out, p, a->H * a->B, st);
+    if (a->dh == 48) return launch_decode_stream<64, 48>(q, k, v, E, out, p, a->H * a->B, st);
+    return launch_decode_stream<32, 32>(q, k, v, E, out, p, a->H * a->B, st);
+  }
   if (a->dh == 64) attn_decode_kernel<64, 64><<<grid, AD_WARPS * 32, 0, st>>>(q, k, v, E, out, p);
   else if (a->dh == 48) attn_decode_kernel<64, 48><<<grid, AD_WARPS * 32, 0, st>>>(q, k, v, E, out, p);
   else attn_decode_kernel<32, 32><<<grid, AD_WARPS * 32, 0, st>>>(q, k, v, E, out, p);

@@ -6,6 +6,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <utility>
 
 namespace me {
 
@@ -116,6 +117,33 @@ __device__ __forceinline__ void dropout_scale4(float p, float inv_keep, uint32_t
   m[1] = (h0 >> 16) >= thr ? inv_keep : 0.f;
   m[2] = (h1 & 0xFFFFu) >= thr ? inv_keep : 0.f;
   m[3] = (h1 >> 16) >= thr ? inv_keep : 0.f;
+}
+
+// ---------------------------------------------------------------------------------
+// Programmatic dependent launch: a kernel launched through launch_pdl() may be scheduled while its predecessor on
+// the stream is still running (after every CTA of the predecessor has executed pdl_launch_dependents(), or exited);
+// it must execute pdl_wait() before its first access to global memory -- the wait returns when the predecessor has
+// completed and its writes are visible.  What overlaps is the launch latency and the prologue (barrier init, TMEM
+// allocation, descriptor prefetch): 2-3 us per launch, which is what the ~100 small kernels of a decode step are
+// made of.  Both instructions are no-ops in a kernel launched the ordinary way.  The attribute is only set with
+// ME_PDL=1: on the B200 decode step it LOST 6 % (see pdl_enabled() in api.cu), the plumbing stays for re-measuring.
+// ---------------------------------------------------------------------------------
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+bool pdl_enabled();
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kern, KArgs(std::forward<Args>(args))...);
 }
 
 // ---------------------------------------------------------------------------------

@@ -197,6 +197,8 @@ add_ln_fwd_kernel(const float* __restrict__ x_res, const T* __restrict__ y, cons
                   float* __restrict__ mean_out, float* __restrict__ rstd_out, const float* __restrict__ src_mean,
                   const float* __restrict__ src_rstd, const float* __restrict__ src_gamma,
                   const float* __restrict__ src_beta) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int lane = threadIdx.x & 31;
   const int wpb = LN_THREADS / 32;
   const int64_t warp0 = static_cast<int64_t>(blockIdx.x) * wpb + (threadIdx.x >> 5);
@@ -462,6 +464,8 @@ __global__ void convert2d_kernel(const TS* __restrict__ src, int ld_src, TD* __r
 template <typename T>
 __global__ void kv_write_kernel(const T* __restrict__ qkv, int B, int Ls, int H, int dh, T* __restrict__ kc,
                                 T* __restrict__ vc, int T_max, int pos0, const int32_t* __restrict__ t_dev) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int d = H * dh;
   const int64_t total = static_cast<int64_t>(B) * Ls * d;
   const int p0 = t_dev ? *t_dev : pos0;
@@ -484,8 +488,8 @@ int launch_kv_write(const void* qkv, int dtype, int B, int Ls, int H, int dh, vo
   const int64_t want = (total + 255) / 256;
   const int blocks = static_cast<int>(want < 148 * 8 ? want : 148 * 8);
   if (dtype == ME_BF16)
-    kv_write_kernel<bf16><<<blocks, 256, 0, st>>>(static_cast<const bf16*>(qkv), B, Ls, H, dh,
-                                                  static_cast<bf16*>(kc), static_cast<bf16*>(vc), T_max, pos0, t_dev);
+    launch_pdl(kv_write_kernel<bf16>, dim3(blocks), dim3(256), 0, st, static_cast<const bf16*>(qkv), B, Ls, H, dh,
+               static_cast<bf16*>(kc), static_cast<bf16*>(vc), T_max, pos0, t_dev);
   else
     kv_write_kernel<float><<<blocks, 256, 0, st>>>(static_cast<const float*>(qkv), B, Ls, H, dh,
                                                    static_cast<float*>(kc), static_cast<float*>(vc), T_max, pos0,
@@ -519,8 +523,8 @@ static int ln_fwd_dispatch(int nch, int blocks, cudaStream_t st, const float* x_
                            T* out_T, float* z, float* mean, float* rstd, const float* src_mean,
                            const float* src_rstd, const float* src_gamma, const float* src_beta) {
 #define ME_LN_FWD(N)                                                                                        \
-  add_ln_fwd_kernel<T, N><<<blocks, LN_THREADS, (src_mean ? 4 : 2) * d * sizeof(float), st>>>(               \
-      x_res, y, gamma, beta, eps, M, d, p, seed, out_f32, out_T, z, mean, rstd, src_mean, src_rstd, src_gamma, src_beta)
+  launch_pdl(add_ln_fwd_kernel<T, N>, dim3(blocks), dim3(LN_THREADS), (src_mean ? 4 : 2) * d * sizeof(float), st, \
+             x_res, y, gamma, beta, eps, M, d, p, seed, out_f32, out_T, z, mean, rstd, src_mean, src_rstd, src_gamma, src_beta)
   switch (nch) {
     case 1: ME_LN_FWD(1); break;
     case 2: ME_LN_FWD(2); break;

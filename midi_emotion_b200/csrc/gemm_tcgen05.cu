@@ -65,10 +65,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     fence_mbar_init();
   }
   if (warp == 1) tmem_alloc(tmem_slot, TMEM_COLS);
+  pdl_launch_dependents();   // the next kernel on the stream may set itself up now ...
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();                // ... and this one touches global memory only once its predecessor has completed
 
   const int total_tiles = p.num_m_tiles * p.num_n_tiles * p.splits;
 
@@ -309,7 +311,7 @@ static int launch_one(const CUtensorMap& tmA, const CUtensorMap& tmB, const Gemm
     ME_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmSmem<BN>::TOTAL));
     configured = true;
   }
-  kern<<<grid, G_THREADS, GemmSmem<BN>::TOTAL, st>>>(tmA, tmB, p);
+  ME_CUDA(launch_pdl(kern, dim3(grid), dim3(G_THREADS), GemmSmem<BN>::TOTAL, st, tmA, tmB, p));
   ME_LAUNCH_CHECK();
   return 0;
 }
