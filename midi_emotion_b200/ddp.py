@@ -5,6 +5,7 @@ averaged across ranks in flat buckets.  The hot path has no other exchange step.
 """
 from __future__ import annotations
 
+import os
 from typing import Iterable, List, Optional
 
 import torch
@@ -61,10 +62,18 @@ class DataParallel:
     and first makes the compute stream wait for reductions an earlier backward pass of the same step started;
     since averaging is linear and idempotent on already-averaged values, avg(avg(g1) + g2) = avg(g1) + avg(g2)."""
 
-    def __init__(self, model: torch.nn.Module, group=None, bucket_mb: float = 256.0, overlap: bool = True):
+    def __init__(self, model: torch.nn.Module, group=None, bucket_mb: float = 256.0, overlap=None):
+        # overlap: True = start each layer's allreduce from the backward pass; "defer" = collect the layers' flat
+        # gradient buffers and reduce them in place, back to back, in sync_gradients(); False = no hook at all.
+        # Default from ME_DDP_OVERLAP (1 / defer / 0), else True.
+        if overlap is None:
+            env = os.environ.get("ME_DDP_OVERLAP", "1")
+            overlap = "defer" if env == "defer" else env != "0"
         self.module = model
         self.group = group
         self.bucket_mb = bucket_mb
+        self.defer = overlap == "defer"
+        self._deferred = []
         self._pending = []
         self.require_backward_grad_sync = True
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
@@ -106,6 +115,10 @@ class DataParallel:
             # `.grad += g` follows on the compute stream: finish what an earlier pass started, forget it (those
             # buffers now hold averaged + local parts and are reduced again, post hoc, by sync_gradients)
             self._drain()
+            self._deferred = []
+            return
+        if self.defer:
+            self._deferred.append(flat)
             return
         if dist.get_backend(self.group) == "nccl":
             work = dist.all_reduce(flat, op=dist.ReduceOp.AVG, group=self.group, async_op=True)
@@ -115,6 +128,12 @@ class DataParallel:
             self._pending.append((flat, work, True))
 
     def _drain(self):
+        for flat in self._deferred:   # reduced in place now, one after the other (no compute runs beside them)
+            if dist.get_backend(self.group) == "nccl":
+                self._pending.append((flat, dist.all_reduce(flat, op=dist.ReduceOp.AVG, group=self.group, async_op=True), False))
+            else:
+                self._pending.append((flat, dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=self.group, async_op=True), True))
+        self._deferred = []
         done = set()
         for flat, work, divide in self._pending:
             work.wait()
