@@ -506,32 +506,40 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
 }
 
 // dsum[b, h, i] = sum_c dO[b, i, h, c] * O[b, i, h, c]   (the "D" term of the softmax backward)
+// Eight lanes per (row, head): lane c multiplies one 16-byte chunk of O with the matching chunk of dO (consecutive
+// lanes read consecutive 16 bytes: whole 128-byte lines per head), three shuffles add the partial dot products.
 template <int DH>
 __global__ void attn_bwd_prep_kernel(const bf16* __restrict__ out, const bf16* __restrict__ dout, int64_t o_sb,
                                      int64_t o_si, int B, int H, int L, float* __restrict__ dsum) {
-  const int64_t idx = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const int64_t t = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const int c = static_cast<int>(t & 7);
+  const int64_t idx = t >> 3;
   const int64_t total = static_cast<int64_t>(B) * L * H;
-  if (idx >= total) return;
-  const int h = static_cast<int>(idx % H);
-  const int64_t bi = idx / H;
-  const int i = static_cast<int>(bi % L);
-  const int b = static_cast<int>(bi / L);
-  const int64_t off = b * o_sb + i * o_si + h * DH;
   float acc = 0.f;
+  int h = 0, i = 0, b = 0;
+  if (idx < total) {
+    h = static_cast<int>(idx % H);
+    const int64_t bi = idx / H;
+    i = static_cast<int>(bi % L);
+    b = static_cast<int>(bi / L);
+    if (c * 8 < DH) {
+      const int64_t off = b * o_sb + i * o_si + h * DH + c * 8;
+      const uint4 uo = __ldg(reinterpret_cast<const uint4*>(out + off));
+      const uint4 ug = __ldg(reinterpret_cast<const uint4*>(dout + off));
+      const __nv_bfloat162* ho = reinterpret_cast<const __nv_bfloat162*>(&uo);
+      const __nv_bfloat162* hg = reinterpret_cast<const __nv_bfloat162*>(&ug);
 #pragma unroll
-  for (int c = 0; c < DH; c += 8) {
-    const uint4 uo = *reinterpret_cast<const uint4*>(out + off + c);
-    const uint4 ug = *reinterpret_cast<const uint4*>(dout + off + c);
-    const __nv_bfloat162* ho = reinterpret_cast<const __nv_bfloat162*>(&uo);
-    const __nv_bfloat162* hg = reinterpret_cast<const __nv_bfloat162*>(&ug);
-#pragma unroll
-    for (int e = 0; e < 4; ++e) {
-      const float2 fo = __bfloat1622float2(ho[e]), fg = __bfloat1622float2(hg[e]);
-      acc = fmaf(fo.x, fg.x, acc);
-      acc = fmaf(fo.y, fg.y, acc);
+      for (int e = 0; e < 4; ++e) {
+        const float2 fo = __bfloat1622float2(ho[e]), fg = __bfloat1622float2(hg[e]);
+        acc = fmaf(fo.x, fg.x, acc);
+        acc = fmaf(fo.y, fg.y, acc);
+      }
     }
   }
-  dsum[(static_cast<int64_t>(b) * H + h) * L + i] = acc;
+  acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+  acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+  acc += __shfl_xor_sync(0xffffffffu, acc, 4);
+  if (c == 0 && idx < total) dsum[(static_cast<int64_t>(b) * H + h) * L + i] = acc;
 }
 
 // dE[e, :] += sum over the private copies of dE_ws[., e, :]
@@ -632,13 +640,13 @@ int launch_attn_bwd_tc(const me_attn_bwd_args* ba) {
   }
   // D = rowsum(dO * O); zero the private dE accumulators
   {
-    const int64_t total = static_cast<int64_t>(B) * L * H;
-    const int blocks = static_cast<int>((total + 127) / 128);
+    const int64_t total = static_cast<int64_t>(B) * L * H * 8;   // eight lanes per (row, head)
+    const int blocks = static_cast<int>((total + 255) / 256);
     const bf16* o = static_cast<const bf16*>(a->out);
     const bf16* g = static_cast<const bf16*>(ba->dout);
-    if (dh == 64) attn_bwd_prep_kernel<64><<<blocks, 128, 0, st>>>(o, g, a->o_sb, a->o_si, B, H, L, ba->dsum);
-    else if (dh == 48) attn_bwd_prep_kernel<48><<<blocks, 128, 0, st>>>(o, g, a->o_sb, a->o_si, B, H, L, ba->dsum);
-    else attn_bwd_prep_kernel<32><<<blocks, 128, 0, st>>>(o, g, a->o_sb, a->o_si, B, H, L, ba->dsum);
+    if (dh == 64) attn_bwd_prep_kernel<64><<<blocks, 256, 0, st>>>(o, g, a->o_sb, a->o_si, B, H, L, ba->dsum);
+    else if (dh == 48) attn_bwd_prep_kernel<48><<<blocks, 256, 0, st>>>(o, g, a->o_sb, a->o_si, B, H, L, ba->dsum);
+    else attn_bwd_prep_kernel<32><<<blocks, 256, 0, st>>>(o, g, a->o_sb, a->o_si, B, H, L, ba->dsum);
     ME_LAUNCH_CHECK();
     ME_CUDA(cudaMemsetAsync(ba->dq_acc, 0, sizeof(float) * static_cast<size_t>(FB_DE_COPIES) * a->max_seq * dh, st));
   }
