@@ -335,7 +335,10 @@ int launch_attn_fwd_tc(const me_attn_args* a) {
            "me_attention_forward: output rows must be 16-byte aligned");
   {
     static const bool two_cta = [] { const char* e = getenv("ME_ATTN_FWD"); return e != nullptr && e[0] == '1'; }();
-    if (!two_cta) return launch_attn_fwd2_tc(a);
+    if (!two_cta) {
+      const int rc = launch_attn_fwd2_tc(a);
+      if (rc >= 0) return rc;
+    }
   }
   CUtensorMap tq, tk, tv, te;
   if (qkv_map(&tq, a->q, a->dh, a->H, a->Lq, a->B, a->q_sh, a->q_si, a->q_sb, FA_BM)) return 1;

@@ -582,14 +582,21 @@ static int launch_fwd2(const CUtensorMap& tq, const CUtensorMap& tk, const CUten
 
 // Unit-claim counters of the persistent kernel: one pair per device, zeroed once (the kernel re-arms them at its
 // end).  Forward launches of one process are stream-ordered on one device, which is what the single pair assumes.
-static int* fwd2_counters() {
+static int* fwd2_counters(cudaStream_t st, bool* capturing) {
   static int* ptr[64] = {};
   int dev = 0;
+  *capturing = false;
   if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) {
     set_error("me_attention_forward: cudaGetDevice failed");
     return nullptr;
   }
   if (ptr[dev] == nullptr) {
+    // (no allocation inside a stream capture: the caller falls back to the two-CTAs-per-SM kernel for that call)
+    cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+    if (cudaStreamIsCapturing(st, &cs) == cudaSuccess && cs != cudaStreamCaptureStatusNone) {
+      *capturing = true;
+      return nullptr;
+    }
     int* q = nullptr;
     if (cudaMalloc(&q, 2 * sizeof(int)) != cudaSuccess || cudaMemset(q, 0, 2 * sizeof(int)) != cudaSuccess) {
       set_error("me_attention_forward: cannot allocate the unit counters");
@@ -600,7 +607,7 @@ static int* fwd2_counters() {
   return ptr[dev];
 }
 
-// (argument checks are done by the caller, launch_attn_fwd_tc)
+// (argument checks are done by the caller, launch_attn_fwd_tc; returns -1 when the caller should use the other kernel)
 int launch_attn_fwd2_tc(const me_attn_args* a) {
   CUtensorMap tq, tk, tv, te;
   if (qkv_map(&tq, a->q, a->dh, a->H, a->Lq, a->B, a->q_sh, a->q_si, a->q_sb, F2_BM)) return 1;
@@ -634,9 +641,10 @@ int launch_attn_fwd2_tc(const me_attn_args* a) {
   }
   p.nq = (a->Lq + F2_BM - 1) / F2_BM;
   p.total_units = p.nq * a->B * a->H;
-  p.counters = fwd2_counters();
+  bool capturing = false;
+  p.counters = fwd2_counters(static_cast<cudaStream_t>(a->stream), &capturing);
   p.trace = g_attn_trace;
-  if (p.counters == nullptr) return 1;
+  if (p.counters == nullptr) return capturing ? -1 : 1;
   const int grid = std::min(sm_count(), p.total_units);
   cudaStream_t st = static_cast<cudaStream_t>(a->stream);
   if (a->flags & ME_ATTN_REF_ROUNDING) {
