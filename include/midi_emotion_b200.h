@@ -94,6 +94,11 @@ int me_embed_forward(const int64_t* tokens, const float* cond, const float* emb_
 int me_embed_backward(const float* dx, const int64_t* tokens, const float* cond, int B, int L, int d,
                       int d_cond, int V, int mode, int pad_token, float dropout_p, uint64_t seed,
                       float* d_emb, float* d_cw0, float* d_cb0, float* d_cw1, float* d_cb1, void* stream);
+/* The same with the gradient given as dx + dx_T (dx_T: bf16 [B, Ls, d] or NULL) -- the two-part gradient
+ * me_layer_backward leaves (me_layer_bwd_args.d_x_T); saves a pass over [M, d] that would add them first. */
+int me_embed_backward_split(const float* dx, const void* dx_T, const int64_t* tokens, const float* cond, int B, int L,
+                            int d, int d_cond, int V, int mode, int pad_token, float dropout_p, uint64_t seed,
+                            float* d_emb, float* d_cw0, float* d_cb0, float* d_cw1, float* d_cb1, void* stream);
 
 /* ---------------------------------------------------------------------------------------
  * Linear layers.  D[M,N] = A . B^T (+ epilogue).  Replaces every torch.nn.Linear on the path

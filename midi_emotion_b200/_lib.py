@@ -114,6 +114,7 @@ _PROTOS = {
     "me_sizeof_decode_layer_args": (C.c_int, []),
     "me_embed_forward": (C.c_int, [_vp] * 8 + [C.c_int] * 7 + [_f32, _u64, C.c_int, _vp, _vp, _vp, _vp]),
     "me_embed_backward": (C.c_int, [_vp] * 3 + [C.c_int] * 7 + [_f32, _u64] + [_vp] * 6),
+    "me_embed_backward_split": (C.c_int, [_vp] * 4 + [C.c_int] * 7 + [_f32, _u64] + [_vp] * 6),
     "me_embed_decode": (C.c_int, [_vp] * 6 + [C.c_int] * 6 + [_vp, C.c_int, _vp, _vp, _vp, C.c_int, _vp]),
     "me_gemm_bf16": (C.c_int, [_vp] * 3 + [C.c_int] * 10 + [_vp, _vp, _vp, C.c_int, _vp]),
     "me_gemm_bf16_ex": (C.c_int, [_vp] * 3 + [C.c_int] * 10 + [_vp, _vp, _vp, C.c_int, C.c_int, C.c_int, _vp]),

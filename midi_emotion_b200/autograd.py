@@ -307,8 +307,8 @@ def backward_stack(model, tokens, cond, a: _Acts, d_x: torch.Tensor, grads: dict
         if hook is not None:
             hook(flat_l)
 
-    if split and d_in_T is not None:
-        d_x.add_(d_in_T)     # the input stage takes the whole gradient in fp32
+    # (the input stage adds the compute-type part of its gradient, d_in_T, itself: me_embed_backward_split)
+    d_x_T_in = d_in_T if split else None
     # input stage
     cw0, cb0, cw1, cb1 = model._cond_params()
     shapes = {"emb": tuple(model.embedding.weight.shape)}
@@ -320,9 +320,9 @@ def backward_stack(model, tokens, cond, a: _Acts, d_x: torch.Tensor, grads: dict
     d_emb = gi["emb"]
     grads["embedding.weight"] = d_emb
     d_c = [gi.get(f"c{i}") for i in range(4)]
-    _lib.call("me_embed_backward", ptr(d_x), ptr(tokens), ptr(cond), B, L, d, model.d_condition, V, model.mode,
-              model.pad_token, a.p, a.seed << 8 | 0xFF, ptr(d_emb), ptr(d_c[0]), ptr(d_c[1]), ptr(d_c[2]),
-              ptr(d_c[3]), stream)
+    _lib.call("me_embed_backward_split", ptr(d_x), ptr(d_x_T_in), ptr(tokens), ptr(cond), B, L, d, model.d_condition,
+              V, model.mode, model.pad_token, a.p, a.seed << 8 | 0xFF, ptr(d_emb), ptr(d_c[0]), ptr(d_c[1]),
+              ptr(d_c[2]), ptr(d_c[3]), stream)
     if hook is not None:
         hook(flat_in)
     if model.continuous_token:

@@ -85,10 +85,13 @@ constexpr int EB_ROWS = 16;
 constexpr int EB_THREADS = 256;
 
 __global__ void __launch_bounds__(EB_THREADS)
-embed_bwd_kernel(const float* __restrict__ dx, const int64_t* __restrict__ tokens, const float* __restrict__ cond,
-                 int B, int L, int d, int dc, int V, int mode, int pad_token, float p, uint64_t seed,
-                 float* __restrict__ d_emb, float* __restrict__ d_cw0, float* __restrict__ d_cb0,
+embed_bwd_kernel(const float* __restrict__ dx, const bf16* __restrict__ dx_T, const int64_t* __restrict__ tokens,
+                 const float* __restrict__ cond, int B, int L, int d, int dc, int V, int mode, int pad_token, float p,
+                 uint64_t seed, float* __restrict__ d_emb, float* __restrict__ d_cw0, float* __restrict__ d_cb0,
                  float* __restrict__ d_cw1, float* __restrict__ d_cb1) {
+  // the gradient w.r.t. the stage's output is dx (+ dx_T: the compute-type part the first layer's QKV projection
+  // leaves, me_layer_bwd_args.d_x_T) -- added here instead of by a separate pass over [M, d]
+  auto gx = [&](int64_t idx) { return dx_T ? dx[idx] + __bfloat162float(dx_T[idx]) : dx[idx]; };
   const bool ctoken = (mode == ME_COND_CONTINUOUS_TOKEN);
   const int Ls = ctoken ? L + 2 : L;
   const int64_t rows = static_cast<int64_t>(B) * Ls;
@@ -109,7 +112,7 @@ embed_bwd_kernel(const float* __restrict__ dx, const int64_t* __restrict__ token
       float* dw = s == 0 ? d_cw0 : d_cw1;
       float* db = s == 0 ? d_cb0 : d_cb1;
       for (int c = threadIdx.x; c < d; c += EB_THREADS) {
-        const float g = dx[row * d + c] * dropout_scale(p, inv_keep, seed, static_cast<uint64_t>(row) * d + c);
+        const float g = gx(row * d + c) * dropout_scale(p, inv_keep, seed, static_cast<uint64_t>(row) * d + c);
         atomicAdd(&dw[c], g * cv);
         atomicAdd(&db[c], g);
       }
@@ -120,7 +123,13 @@ embed_bwd_kernel(const float* __restrict__ dx, const int64_t* __restrict__ token
     float* erow = d_emb + tok * de;
     if (vec) {
       for (int c = 4 * threadIdx.x; c < de; c += 4 * EB_THREADS) {
-        const float4 g = *reinterpret_cast<const float4*>(dx + row * d + c);
+        float4 g = *reinterpret_cast<const float4*>(dx + row * d + c);
+        if (dx_T) {
+          const uint2 u = *reinterpret_cast<const uint2*>(dx_T + row * d + c);
+          const float2 t0 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u.x));
+          const float2 t1 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u.y));
+          g.x += t0.x; g.y += t0.y; g.z += t1.x; g.w += t1.y;
+        }
         float dm[4];
         dropout_scale4(p, inv_keep, seed32, static_cast<uint64_t>(row) * d + c, dm);
         atomicAdd(reinterpret_cast<float4*>(erow + c),
@@ -128,7 +137,7 @@ embed_bwd_kernel(const float* __restrict__ dx, const int64_t* __restrict__ token
       }
     } else {
       for (int c = threadIdx.x; c < de; c += EB_THREADS)
-        atomicAdd(&erow[c], dx[row * d + c] * scale * dropout_scale(p, inv_keep, seed, static_cast<uint64_t>(row) * d + c));
+        atomicAdd(&erow[c], gx(row * d + c) * scale * dropout_scale(p, inv_keep, seed, static_cast<uint64_t>(row) * d + c));
     }
   }
   // ---- concatenated condition columns: Linear(2, dc), summed over this block's rows
@@ -137,7 +146,7 @@ embed_bwd_kernel(const float* __restrict__ dx, const int64_t* __restrict__ token
       float a0 = 0.f, a1 = 0.f, ab = 0.f;
       for (int64_t row = r0; row < r1; ++row) {
         const int b = static_cast<int>(row / Ls);
-        const float g = dx[row * d + de + j] *
+        const float g = gx(row * d + de + j) *
                         dropout_scale(p, inv_keep, seed, static_cast<uint64_t>(row) * d + de + j);
         a0 = fmaf(g, cond[b * 2 + 0], a0);
         a1 = fmaf(g, cond[b * 2 + 1], a1);
@@ -749,16 +758,27 @@ extern "C" int me_embed_decode(const int64_t* tokens, const float* cond, const f
                       0.f, 0, t_dev, T_max, dtype, x_f32, x_T, keypad, static_cast<cudaStream_t>(stream));
 }
 
+extern "C" int me_embed_backward_split(const float* dx, const void* dx_T, const int64_t* tokens, const float* cond,
+                                       int B, int L, int d, int d_cond, int V, int mode, int pad_token,
+                                       float dropout_p, uint64_t seed, float* d_emb, float* d_cw0, float* d_cb0,
+                                       float* d_cw1, float* d_cb1, void* stream) {
+  ME_CHECK(dx_T == nullptr || ((reinterpret_cast<uintptr_t>(dx_T) & 7) == 0 && d % 4 == 0),
+           "me_embed_backward_split: dx_T needs 8-byte alignment and d a multiple of 4");
+  const int Ls = mode == ME_COND_CONTINUOUS_TOKEN ? L + 2 : L;
+  const int64_t rows = static_cast<int64_t>(B) * Ls;
+  embed_bwd_kernel<<<static_cast<int>((rows + EB_ROWS - 1) / EB_ROWS), EB_THREADS, 0, static_cast<cudaStream_t>(stream)>>>(
+      dx, static_cast<const bf16*>(dx_T), tokens, cond, B, L, d, d_cond, V, mode, pad_token, dropout_p, seed, d_emb,
+      d_cw0, d_cb0, d_cw1, d_cb1);
+  ME_LAUNCH_CHECK();
+  return 0;
+}
+
 extern "C" int me_embed_backward(const float* dx, const int64_t* tokens, const float* cond, int B, int L, int d,
                                  int d_cond, int V, int mode, int pad_token, float dropout_p, uint64_t seed,
                                  float* d_emb, float* d_cw0, float* d_cb0, float* d_cw1, float* d_cb1,
                                  void* stream) {
-  const int Ls = mode == ME_COND_CONTINUOUS_TOKEN ? L + 2 : L;
-  const int64_t rows = static_cast<int64_t>(B) * Ls;
-  embed_bwd_kernel<<<static_cast<int>((rows + EB_ROWS - 1) / EB_ROWS), EB_THREADS, 0, static_cast<cudaStream_t>(stream)>>>(
-      dx, tokens, cond, B, L, d, d_cond, V, mode, pad_token, dropout_p, seed, d_emb, d_cw0, d_cb0, d_cw1, d_cb1);
-  ME_LAUNCH_CHECK();
-  return 0;
+  return me_embed_backward_split(dx, nullptr, tokens, cond, B, L, d, d_cond, V, mode, pad_token, dropout_p, seed, d_emb,
+                                 d_cw0, d_cb0, d_cw1, d_cb1, stream);
 }
 
 extern "C" int me_add_layernorm_forward(const float* x_res, const void* y, int dtype, const float* gamma,
