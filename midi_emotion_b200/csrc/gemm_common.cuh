@@ -17,6 +17,7 @@ struct GemmParams {
   const float* addend;
   const void* relu_mask;
   void* D;
+  float* colsum;   // staged bf16 epilogue of the pair kernel: colsum[n] += sum over rows of the stored output, or NULL
 };
 
 

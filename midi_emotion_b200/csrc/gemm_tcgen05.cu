@@ -318,11 +318,14 @@ static int launch_one(const CUtensorMap& tmA, const CUtensorMap& tmB, const Gemm
 
 int launch_gemm_bf16_pair(const void* A, const void* B, void* D, int M, int N, int K, int lda, int ldb, int ldd,
                           int a_mn, int b_mn, int out_dtype, int flags, const float* bias, const float* addend,
-                          const void* relu_mask, int ldmask, int force_splits, cudaStream_t st);
+                          const void* relu_mask, int ldmask, int force_splits, cudaStream_t st, float* colsum_out,
+                          bool* colsum_done);
 
 int launch_gemm_bf16(const void* A, const void* B, void* D, int M, int N, int K, int lda, int ldb, int ldd,
                      int a_mn, int b_mn, int out_dtype, int flags, const float* bias, const float* addend,
-                     const void* relu_mask, int ldmask, int force_bn, int force_splits, cudaStream_t st) {
+                     const void* relu_mask, int ldmask, int force_bn, int force_splits, cudaStream_t st,
+                     float* colsum_out, bool* colsum_done) {
+  if (colsum_done) *colsum_done = false;
   ME_CHECK(M > 0 && N > 0 && K > 0, "me_gemm_bf16: bad dims M=%d N=%d K=%d", M, N, K);
   ME_CHECK(lda % 8 == 0 && ldb % 8 == 0, "me_gemm_bf16: operand row pitches must be multiples of 8 elements (lda=%d ldb=%d)", lda, ldb);
   ME_CHECK((reinterpret_cast<uintptr_t>(A) & 15) == 0 && (reinterpret_cast<uintptr_t>(B) & 15) == 0,
@@ -344,7 +347,8 @@ int launch_gemm_bf16(const void* A, const void* B, void* D, int M, int N, int K,
   // CTA-pair kernel (256 x 256 tiles, cta_group::2) whenever the problem fills the machine with them
   if (force_bn == 0 || force_bn == 512) {
     const int rc = launch_gemm_bf16_pair(A, B, D, M, N, K, lda, ldb, ldd, a_mn, b_mn, out_dtype, flags, bias, addend,
-                                         relu_mask, ldmask, force_bn == 512 ? (force_splits > 0 ? force_splits : -1) : 0, st);
+                                         relu_mask, ldmask, force_bn == 512 ? (force_splits > 0 ? force_splits : -1) : 0, st,
+                                         colsum_out, colsum_done);
     if (rc >= 0) return rc;
     ME_CHECK(force_bn != 512, "me_gemm_bf16: the CTA-pair kernel does not take this shape");
   }
@@ -395,6 +399,7 @@ int launch_gemm_bf16(const void* A, const void* B, void* D, int M, int N, int K,
   p.M = M; p.N = N; p.K = K; p.ldd = ldd; p.ldmask = ldmask; p.flags = flags; p.out_dtype = out_dtype;
   p.num_m_tiles = num_m_tiles; p.num_n_tiles = num_n_tiles; p.splits = splits; p.kb_per_split = kb_per;
   p.num_kb = num_kb; p.bias = bias; p.addend = addend; p.relu_mask = relu_mask; p.D = D;
+  p.colsum = nullptr;
   if (splits > 1) {
     ME_CUDA(cudaMemsetAsync(D, 0, static_cast<size_t>(M) * ldd * sizeof(float), st));
   }
@@ -427,7 +432,7 @@ extern "C" int me_gemm_bf16(const void* A, const void* B, void* D, int M, int N,
                             int a_mn, int b_mn, int out_dtype, int epi_flags, const float* bias,
                             const float* addend, const void* relu_mask, int ldmask, void* stream) {
   return me::launch_gemm_bf16(A, B, D, M, N, K, lda, ldb, ldd, a_mn, b_mn, out_dtype, epi_flags, bias, addend,
-                              relu_mask, ldmask, 0, 0, static_cast<cudaStream_t>(stream));
+                              relu_mask, ldmask, 0, 0, static_cast<cudaStream_t>(stream), nullptr, nullptr);
 }
 
 // test/tuning hook: force the tile width and split count
@@ -436,5 +441,5 @@ extern "C" int me_gemm_bf16_ex(const void* A, const void* B, void* D, int M, int
                                const float* addend, const void* relu_mask, int ldmask, int tile_n, int splits,
                                void* stream) {
   return me::launch_gemm_bf16(A, B, D, M, N, K, lda, ldb, ldd, a_mn, b_mn, out_dtype, epi_flags, bias, addend,
-                              relu_mask, ldmask, tile_n, splits, static_cast<cudaStream_t>(stream));
+                              relu_mask, ldmask, tile_n, splits, static_cast<cudaStream_t>(stream), nullptr, nullptr);
 }

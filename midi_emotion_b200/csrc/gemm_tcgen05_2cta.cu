@@ -306,6 +306,19 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             if (n0 + blk * 64 < p.N && m0 < p.M) tma_store_2d(&tmD, stg + blk * 16384, n0 + blk * 64, m0);
           bulk_commit();
         }
+        if (p.colsum != nullptr && n0 + et < p.N) {
+          // column sums of the tile as stored (bf16-rounded): the bias gradient of the Linear whose output gradient
+          // this GEMM produces -- thread = column, rows straight out of the staging tile (a warp reads 64 contiguous
+          // bytes of a row: no bank conflicts), one atomic per column and tile instead of a second pass over [M, N]
+          const uint8_t* col = stg + (et >> 6) * 16384 + (et & 7) * 2;
+          const int q = (et & 63) >> 3;
+          const int rows = min(128, p.M - m0);
+          float sum = 0.f;
+#pragma unroll 8
+          for (int r = 0; r < rows; ++r)
+            sum += __bfloat162float(*reinterpret_cast<const bf16*>(col + r * 128 + ((q ^ (r & 7)) << 4)));
+          atomicAdd(&p.colsum[n0 + et], sum);
+        }
       }
     }
     if (STAGED && et == 0) bulk_wait_all();
@@ -338,7 +351,9 @@ int g_pair_force_direct = 0;  // test hook: 1 = never use the staged epilogue
 // Returns 0 on success, 1 on error, -1 when the shape is better served by the 1-CTA kernel.
 int launch_gemm_bf16_pair(const void* A, const void* B, void* D, int M, int N, int K, int lda, int ldb, int ldd,
                           int a_mn, int b_mn, int out_dtype, int flags, const float* bias, const float* addend,
-                          const void* relu_mask, int ldmask, int force_splits, cudaStream_t st) {
+                          const void* relu_mask, int ldmask, int force_splits, cudaStream_t st, float* colsum_out,
+                          bool* colsum_done) {
+  if (colsum_done) *colsum_done = false;
   if (a_mn && !b_mn) return -1;
   const int sms = sm_count();
   const int pairs = sms / 2;
@@ -372,6 +387,7 @@ int launch_gemm_bf16_pair(const void* A, const void* B, void* D, int M, int N, i
   p.M = M; p.N = N; p.K = K; p.ldd = ldd; p.ldmask = ldmask; p.flags = flags; p.out_dtype = out_dtype;
   p.num_m_tiles = num_m_tiles; p.num_n_tiles = num_n_tiles; p.splits = splits; p.kb_per_split = kb_per;
   p.num_kb = num_kb; p.bias = bias; p.addend = addend; p.relu_mask = relu_mask; p.D = D;
+  p.colsum = nullptr;
   if (splits > 1) ME_CUDA(cudaMemsetAsync(D, 0, static_cast<size_t>(M) * ldd * sizeof(float), st));
   const int total = tiles * splits;
   const int grid = 2 * (total < pairs ? total : pairs);
@@ -386,6 +402,10 @@ int launch_gemm_bf16_pair(const void* A, const void* B, void* D, int M, int N, i
     if (flags & ME_EPI_RELU_MASK) {
       if (make_tmap_2d_bf16(&tmMask, relu_mask, N, M, ldmask, 64, 128)) return 1;
     }
+  }
+  if (staged && colsum_out != nullptr) {
+    p.colsum = colsum_out;
+    if (colsum_done) *colsum_done = true;
   }
   cudaEvent_t pe = prof_begin(2.0 * M * N * K, st);
   int rc;

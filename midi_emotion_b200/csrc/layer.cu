@@ -7,7 +7,8 @@ namespace me {
 
 int launch_gemm_bf16(const void* A, const void* B, void* D, int M, int N, int K, int lda, int ldb, int ldd,
                      int a_mn, int b_mn, int out_dtype, int flags, const float* bias, const float* addend,
-                     const void* relu_mask, int ldmask, int force_bn, int force_splits, cudaStream_t st);
+                     const void* relu_mask, int ldmask, int force_bn, int force_splits, cudaStream_t st,
+                     float* colsum_out, bool* colsum_done);
 int launch_gemm_f32(const float* A, const float* B, float* D, int M, int N, int K, int lda, int ldb, int ldd,
                     int a_mn, int b_mn, int flags, const float* bias, const float* addend,
                     const float* relu_mask, int ldmask, cudaStream_t st);
@@ -27,13 +28,15 @@ int launch_kv_write(const void* qkv, int dtype, int B, int Ls, int H, int dh, vo
 // D = A . B^T in the layer's compute type.  out_f32 forces an fp32 result (residual-stream gradients).
 static int linear(int dtype, const void* A, const void* B, void* D, int M, int N, int K, int lda, int ldb, int ldd,
                   int a_mn, int b_mn, bool out_f32, int flags, const float* bias, const float* addend,
-                  const void* relu_mask, int ldmask, cudaStream_t st) {
+                  const void* relu_mask, int ldmask, cudaStream_t st, float* colsum_out = nullptr,
+                  bool* colsum_done = nullptr) {
+  if (colsum_done) *colsum_done = false;
   if (dtype == ME_F32)
     return launch_gemm_f32(static_cast<const float*>(A), static_cast<const float*>(B), static_cast<float*>(D), M, N,
                            K, lda, ldb, ldd, a_mn, b_mn, flags, bias, addend,
                            static_cast<const float*>(relu_mask), ldmask, st);
   return launch_gemm_bf16(A, B, D, M, N, K, lda, ldb, ldd, a_mn, b_mn, out_f32 ? ME_F32 : ME_BF16, flags, bias,
-                          addend, relu_mask, ldmask, 0, 0, st);
+                          addend, relu_mask, ldmask, 0, 0, st, colsum_out, colsum_done);
 }
 
 static inline size_t esize(int dtype) { return dtype == ME_BF16 ? 2 : 4; }
@@ -181,13 +184,15 @@ extern "C" int me_layer_backward(const me_layer_bwd_args* b) {
     return 1;
   // dW2[d, di] = g_T^T . h
   if (linear(dt, b->g_T, a->h, b->dW2, d, di, M, d, di, di, 1, 1, true, 0, nullptr, nullptr, nullptr, 0, st)) return 1;
-  // g_h[M, di] = (g_T . W2) masked by relu
+  // g_h[M, di] = (g_T . W2) masked by relu; db1 = its column sums, taken from the staged output tiles by the GEMM's
+  // epilogue when that path runs (bf16), else by a pass over g_h
+  bool db1_done = false;
   if (linear(dt, b->g_T, a->W2, b->g_h, M, di, d, d, di, di, 0, 1, false, ME_EPI_RELU_MASK, nullptr, nullptr, a->h,
-             di, st))
+             di, st, b->db1, &db1_done))
     return 1;
   // (the attention workspace is idle outside me_attention_backward: scratch for the partial column sums)
   const int64_t ws_floats = b->attn_ws ? me_attention_backward_workspace_floats(a->B, H, a->Ls, dh, a->max_seq) : 0;
-  if (launch_colsum_ws(b->g_h, dt, M, di, di, b->db1, b->attn_ws, ws_floats, st)) return 1;
+  if (!db1_done && launch_colsum_ws(b->g_h, dt, M, di, di, b->db1, b->attn_ws, ws_floats, st)) return 1;
   // dW1[di, d] = g_h^T . out1
   if (linear(dt, b->g_h, a->out1_T, b->dW1, di, d, M, di, d, d, 1, 1, true, 0, nullptr, nullptr, nullptr, 0, st))
     return 1;
