@@ -170,9 +170,12 @@ def _uniform_row_pitch(t: torch.Tensor):
     return ld if ld >= t.shape[-1] else None
 
 
-def run_backward(model, tokens, cond, a: _Acts, g_logits: torch.Tensor, ld_g: Optional[int] = None) -> List[Optional[torch.Tensor]]:
+def run_backward(model, tokens, cond, a: _Acts, g_logits: torch.Tensor, ld_g: Optional[int] = None,
+                 g_scale: Optional[torch.Tensor] = None) -> List[Optional[torch.Tensor]]:
     """g_logits: M rows of V gradient values in the compute type at row pitch ld_g (default Vp; columns >= V are
-    never read).  Returns gradients in named_parameters() order."""
+    never read).  g_scale (device scalar, optional): the gradients are those of g_scale * g_logits -- applied to the
+    head's small tensors (its weight copy, dW, db) instead of in a pass over the [M, V] tensor.
+    Returns gradients in named_parameters() order."""
     dtype = a.dtype
     tdt = _tdtype(dtype)
     dev = tokens.device
@@ -197,16 +200,21 @@ def run_backward(model, tokens, cond, a: _Acts, g_logits: torch.Tensor, ld_g: Op
     d_x = torch.empty(M, d, **f32)
     cs_ws = torch.empty(160 * V, **f32)     # partial rows of the column sums (no same-address atomics)
     _lib.call("me_colsum_ws", ptr(g_logits), dtype, M, V, ld_g, ptr(grads["fc.bias"]), ptr(cs_ws), cs_ws.numel(), stream)
+    Wfc = wc["Wfc"]
+    if g_scale is not None:     # dx = g (s W): scale the [V, d] weight copy, not the [M, V] gradient
+        Wfc = (Wfc.float() * g_scale).to(Wfc.dtype)
     if dtype == ME_BF16:
         _lib.call("me_gemm_bf16", ptr(g_logits), ptr(last["out2_T"]), ptr(grads["fc.weight"]), V, d, M, ld_g, d, d, 1, 1,
                   ME_F32, 0, None, None, None, 0, stream)
-        _lib.call("me_gemm_bf16", ptr(g_logits), ptr(wc["Wfc"]), ptr(d_x), M, d, V, ld_g, d, d, 0, 1, ME_F32, 0, None,
+        _lib.call("me_gemm_bf16", ptr(g_logits), ptr(Wfc), ptr(d_x), M, d, V, ld_g, d, d, 0, 1, ME_F32, 0, None,
                   None, None, 0, stream)
     else:
         _lib.call("me_gemm_f32", ptr(g_logits), ptr(last["out2_T"]), ptr(grads["fc.weight"]), V, d, M, ld_g, d, d, 1, 1,
                   0, None, None, None, 0, stream)
-        _lib.call("me_gemm_f32", ptr(g_logits), ptr(wc["Wfc"]), ptr(d_x), M, d, V, ld_g, d, d, 0, 1, 0, None, None,
+        _lib.call("me_gemm_f32", ptr(g_logits), ptr(Wfc), ptr(d_x), M, d, V, ld_g, d, d, 0, 1, 0, None, None,
                   None, 0, stream)
+    if g_scale is not None:
+        flat_head.mul_(g_scale)     # dW and db of the head
     if hook is not None:
         hook(flat_head)
     backward_stack(model, tokens, cond, a, d_x, grads)
@@ -398,8 +406,9 @@ class _ModelLossFn(torch.autograd.Function):
         model, a, grad = ctx.model, ctx.acts, ctx.grad
         if grad is None or a.layers is None or a.layers[0] is None or "z1" not in a.layers[0]:
             raise RuntimeError("midi_emotion_b200: backward called twice or forward ran without grad")
-        grad.mul_(g_loss)      # d(mean loss)/d(logits) was written by the forward kernel; pad columns are zero
-        grads = run_backward(model, ctx.tokens, ctx.cond, a, grad, a.Vp)
+        # d(mean loss)/d(logits) was written by the forward kernel (pad columns are zero); the upstream gradient of
+        # the scalar loss is applied inside run_backward on the head's small tensors
+        grads = run_backward(model, ctx.tokens, ctx.cond, a, grad, a.Vp, g_scale=g_loss)
         ctx.acts = ctx.grad = None
         return (None, None, None, None, None, None, *grads)
 
