@@ -273,9 +273,17 @@ attn_decode_stream_kernel(const bf16* __restrict__ q, const bf16* __restrict__ k
     return;
   }
 
+  // Chunk cc of this lane is chunk g + 4 (cc ^ sw) of the row: the odd key slots take their two chunks in the other
+  // order, so that the eight lanes of a quarter-warp (two key slots, rows 128 bytes apart) read 128 distinct bytes
+  // per load instead of hitting the same banks twice.
+  const int sw = (NC == 2) ? (kslot & 1) : 0;
+  int cix[NC];
   bool live[NC];
 #pragma unroll
-  for (int c = 0; c < NC; ++c) live[c] = 8 * (g + 4 * c) < DH;
+  for (int c = 0; c < NC; ++c) {
+    cix[c] = g + 4 * (c ^ sw);
+    live[c] = 8 * cix[c] < DH;
+  }
 
   int G = 0;
   for (int it = 0; it < my_items; ++it) {
@@ -288,7 +296,7 @@ attn_decode_stream_kernel(const bf16* __restrict__ q, const bf16* __restrict__ k
 #pragma unroll
       for (int c = 0; c < NC; ++c) {
         uint4 u = make_uint4(0, 0, 0, 0);
-        if (live[c]) u = __ldg(reinterpret_cast<const uint4*>(qrow) + g + 4 * c);
+        if (live[c]) u = __ldg(reinterpret_cast<const uint4*>(qrow) + cix[c]);
         const uint32_t w[4] = {u.x, u.y, u.z, u.w};
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
@@ -317,7 +325,7 @@ attn_decode_stream_kernel(const bf16* __restrict__ q, const bf16* __restrict__ k
         for (int cc = 0; cc < NC; ++cc) {
           kr[cc] = er[cc] = vr[cc] = make_uint4(0, 0, 0, 0);
           if (live[cc] && j <= t) {
-            const int off = jr * ROW + (g + 4 * cc) * 16;
+            const int off = jr * ROW + cix[cc] * 16;
             kr[cc] = *reinterpret_cast<const uint4*>(st + off);
             er[cc] = *reinterpret_cast<const uint4*>(st + 2 * TILE + off);
             vr[cc] = *reinterpret_cast<const uint4*>(st + TILE + off);
@@ -352,6 +360,14 @@ attn_decode_stream_kernel(const bf16* __restrict__ q, const bf16* __restrict__ k
     }
 
     // merge the 8 key slots of the warp (lanes with equal g), then the warps of the block
+    if (NC == 2) {   // back to the common chunk order first
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
+        const float lo = o[c], hi = o[8 + c];
+        o[c] = sw ? hi : lo;
+        o[8 + c] = sw ? lo : hi;
+      }
+    }
     float wm = m;
 #pragma unroll
     for (int sft = 4; sft <= 16; sft <<= 1) wm = fmaxf(wm, __shfl_xor_sync(0xffffffffu, wm, sft));
